@@ -1,0 +1,212 @@
+// state_ops.cuh -- register-level state math shared by every kernel (and by tests/host_check.cpp).
+//
+// A state of S bytes lives in W = 2*ceil(S/8) little-endian u32 words with the bytes past S zeroed, so the
+// words feed the hash directly.  Everything here is branch-free straight-line code after unrolling: move
+// application never indexes registers dynamically.
+#pragma once
+#include "cube3_moves.cuh"
+#include "intrinsics.cuh"
+
+namespace dcb {
+
+constexpr int kEnvCube3 = 0;
+
+template <int ENV> struct EnvTraits;
+template <> struct EnvTraits<0> { static constexpr int S = 54, A = 12, DIM = 3; static constexpr bool kPuzzle = false; };
+template <> struct EnvTraits<1> { static constexpr int S = 16, A = 4, DIM = 4; static constexpr bool kPuzzle = true; };
+template <> struct EnvTraits<2> { static constexpr int S = 25, A = 4, DIM = 5; static constexpr bool kPuzzle = true; };
+template <> struct EnvTraits<3> { static constexpr int S = 36, A = 4, DIM = 6; static constexpr bool kPuzzle = true; };
+template <> struct EnvTraits<4> { static constexpr int S = 49, A = 4, DIM = 7; static constexpr bool kPuzzle = true; };
+
+constexpr int hash_words(int s) { return 2 * ((s + 7) / 8); }
+constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) ? 2 : 1); }
+
+// ---------------------------------------------------------------------------------------------------
+// Hash: NH pair-product universal hash (keys from splitmix64, see oracle/oracle_env.py) + murmur3 fmix64.
+// On sm_100a each term is one IMAD.WIDE.U32 with 64-bit accumulate; the adds are IADD3.
+// ---------------------------------------------------------------------------------------------------
+constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;
+DCB_HOSTDEV constexpr uint32_t hash_key(int i) {
+  constexpr uint32_t k[16] = {0xa82e9745u, 0x275e0ca1u, 0xa22c9073u, 0x922741ddu, 0x98b201b5u, 0xebbdc7b7u,
+                              0xed62b2c5u, 0xdedc17fbu, 0x963a6a25u, 0xa4b0b7d7u, 0xd613fdbfu, 0xd5658cfdu,
+                              0x6b33c2a1u, 0x7a9e4ccbu, 0x3ae98f97u, 0x6d554fd7u};
+  return k[i];
+}
+
+DCB_HOSTDEV uint64_t fmix64(uint64_t h) {
+  h ^= h >> 33; h *= 0xFF51AFD7ED558CCDull;
+  h ^= h >> 33; h *= 0xC4CEB9FE1A85EC53ull;
+  h ^= h >> 33;
+  return h ? h : 1ull;   // 0 is the closed table's EMPTY key
+}
+
+template <int W> DCB_DEV uint64_t state_hash(const uint32_t (&w)[W]) {
+  static_assert(W % 2 == 0 && W <= 16, "hash words");
+  uint64_t acc = kHashSeed;
+#pragma unroll
+  for (int i = 0; i < W; i += 2)
+    acc += (uint64_t)(uint32_t)(w[i] + hash_key(i)) * (uint64_t)(uint32_t)(w[i + 1] + hash_key(i + 1));
+  return fmix64(acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Goal states
+// ---------------------------------------------------------------------------------------------------
+template <int ENV> DCB_HOSTDEV constexpr uint8_t goal_byte(int j) {
+  // cube3: sticker identity (cube3.py:37, :71-75).  n-puzzle: [1..n*n-1, 0] (n_puzzle.py:41).
+  return ENV == 0 ? (uint8_t)j : (uint8_t)((j + 1) % EnvTraits<ENV>::S);
+}
+template <int ENV> DCB_HOSTDEV constexpr uint32_t goal_word(int w) {
+  constexpr int S = EnvTraits<ENV>::S;
+  uint32_t v = 0;
+  for (int b = 0; b < 4; b++) {
+    const int j = 4 * w + b;
+    if (j < S) v |= (uint32_t)goal_byte<ENV>(j) << (8 * b);
+  }
+  return v;
+}
+template <int ENV, int W> DCB_DEV bool is_goal(const uint32_t (&w)[W]) {
+  uint32_t diff = 0;
+#pragma unroll
+  for (int i = 0; i < W; i++) diff |= w[i] ^ goal_word<ENV>(i);
+  return diff == 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Static byte shifts of a W-word little-endian byte array (bytes shifted out are lost, zeros shifted in)
+// ---------------------------------------------------------------------------------------------------
+template <int W, int K> DCB_DEV void shift_up_bytes(const uint32_t (&in)[W], uint32_t (&out)[W]) {
+  constexpr int q = K / 4, r = K % 4;   // out byte j = in byte j-K
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const uint32_t hi = (w - q >= 0) ? in[(w - q >= 0) ? w - q : 0] : 0u;
+    const uint32_t lo = (w - q - 1 >= 0) ? in[(w - q - 1 >= 0) ? w - q - 1 : 0] : 0u;
+    out[w] = (r == 0) ? hi : __funnelshift_l(lo, hi, 8 * r);
+  }
+}
+template <int W, int K> DCB_DEV void shift_down_bytes(const uint32_t (&in)[W], uint32_t (&out)[W]) {
+  constexpr int q = K / 4, r = K % 4;   // out byte j = in byte j+K
+#pragma unroll
+  for (int w = 0; w < W; w++) {
+    const uint32_t lo = (w + q < W) ? in[(w + q < W) ? w + q : 0] : 0u;
+    const uint32_t hi = (w + q + 1 < W) ? in[(w + q + 1 < W) ? w + q + 1 : 0] : 0u;
+    out[w] = (r == 0) ? lo : __funnelshift_r(lo, hi, 8 * r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// n-puzzle: all four children of one parent, SIMD-within-register.
+//   moves U,D,L,R swap the blank with the tile at (i+1,j),(i-1,j),(i,j+1),(i,j-1); an illegal move leaves
+//   the state unchanged (n_puzzle.py:174-231; cpp/environments.cpp:4-46, 92-104).
+//   zmask marks the blank byte; shifting it by +-DIM / +-1 bytes marks the tile to swap; XOR-ing the tile
+//   value into both positions performs the swap.  No table, no dynamic byte indexing.
+// ---------------------------------------------------------------------------------------------------
+template <int DIM> DCB_HOSTDEV constexpr uint32_t col_mask(int w, int excluded_col) {
+  // 0xFF for every byte j < DIM*DIM in word w whose column (j % DIM) != excluded_col
+  uint32_t v = 0;
+  for (int b = 0; b < 4; b++) {
+    const int j = 4 * w + b;
+    if (j < DIM * DIM && (j % DIM) != excluded_col) v |= 0xFFu << (8 * b);
+  }
+  return v;
+}
+template <int S> DCB_HOSTDEV constexpr uint32_t valid_mask(int w) {
+  uint32_t v = 0;
+  for (int b = 0; b < 4; b++)
+    if (4 * w + b < S) v |= 0xFFu << (8 * b);
+  return v;
+}
+
+template <int DIM, int MOVE, int W> DCB_DEV void puzzle_child(const uint32_t (&p)[W], const uint32_t (&zm)[W], uint32_t (&c)[W]) {
+  constexpr int S = DIM * DIM;
+  uint32_t z[W], sm[W], t[W], tz[W];
+  if (MOVE == 0) {          // U: swap with byte z + DIM
+#pragma unroll
+    for (int w = 0; w < W; w++) z[w] = zm[w];
+    shift_up_bytes<W, DIM>(z, sm);
+  } else if (MOVE == 1) {   // D: swap with byte z - DIM
+#pragma unroll
+    for (int w = 0; w < W; w++) z[w] = zm[w];
+    shift_down_bytes<W, DIM>(z, sm);
+  } else if (MOVE == 2) {   // L: swap with byte z + 1, only if the blank is not in the last column
+#pragma unroll
+    for (int w = 0; w < W; w++) z[w] = zm[w] & col_mask<DIM>(w, DIM - 1);
+    shift_up_bytes<W, 1>(z, sm);
+  } else {                  // R: swap with byte z - 1, only if the blank is not in the first column
+#pragma unroll
+    for (int w = 0; w < W; w++) z[w] = zm[w] & col_mask<DIM>(w, 0);
+    shift_down_bytes<W, 1>(z, sm);
+  }
+#pragma unroll
+  for (int w = 0; w < W; w++) t[w] = p[w] & sm[w] & valid_mask<S>(w);   // tile value at its own position
+  if (MOVE == 0) shift_down_bytes<W, DIM>(t, tz);
+  else if (MOVE == 1) shift_up_bytes<W, DIM>(t, tz);
+  else if (MOVE == 2) shift_down_bytes<W, 1>(t, tz);
+  else shift_up_bytes<W, 1>(t, tz);
+#pragma unroll
+  for (int w = 0; w < W; w++) c[w] = p[w] ^ t[w] ^ tz[w];
+}
+
+template <int DIM, int W> DCB_DEV void puzzle_blank_mask(const uint32_t (&p)[W], uint32_t (&zm)[W]) {
+#pragma unroll
+  for (int w = 0; w < W; w++) zm[w] = __vcmpeq4(p[w], 0u) & valid_mask<DIM * DIM>(w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Generic single child: ENV, MOVE compile-time
+// ---------------------------------------------------------------------------------------------------
+template <int ENV, int MOVE, int W> struct ChildOf;
+template <int MOVE> struct ChildOf<0, MOVE, 14> {
+  static DCB_DEV void apply(const uint32_t (&p)[14], const uint32_t (&)[14], uint32_t (&c)[14]) { cube3_move<MOVE>(p, c); }
+};
+template <int ENV, int MOVE, int W> struct ChildOf {
+  static DCB_DEV void apply(const uint32_t (&p)[W], const uint32_t (&zm)[W], uint32_t (&c)[W]) {
+    puzzle_child<EnvTraits<ENV>::DIM, MOVE, W>(p, zm, c);
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// Record packing: NC consecutive children of S bytes each, given as aligned W-word arrays (bytes >= S
+// zero), concatenated without padding into NC*S/4 record words.
+// ---------------------------------------------------------------------------------------------------
+template <int S, int W> DCB_DEV uint32_t bytes_at(const uint32_t (&x)[W], int o) {
+  // 4 bytes of x starting at (static) byte offset o; bytes past the array read as 0
+  const int q = o / 4, r = o % 4;
+  const uint32_t lo = (q < W) ? x[(q < W) ? q : 0] : 0u;
+  const uint32_t hi = (q + 1 < W) ? x[(q + 1 < W) ? q + 1 : 0] : 0u;
+  return (r == 0) ? lo : __funnelshift_r(lo, hi, 8 * r);
+}
+
+template <int S, int NC, int W> DCB_DEV void pack_record(const uint32_t (&ch)[NC][W], uint32_t (&rec)[NC * S / 4]) {
+  static_assert((NC * S) % 4 == 0, "record must be a whole number of words");
+#pragma unroll
+  for (int k = 0; k < NC * S / 4; k++) {
+    const int c = (4 * k) / S, o = 4 * k - S * c;
+    uint32_t v = bytes_at<S, W>(ch[c], o);
+    if (o + 4 > S) {                       // straddles into child c+1 (bytes past S of child c are zero)
+      const int n0 = S - o;
+      v |= ch[(c + 1 < NC) ? c + 1 : c][0] << (8 * n0);
+    }
+    rec[k] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Loading a state from a byte address with arbitrary (env-dependent) alignment into aligned words.
+// raw[] must hold NRAW = (S + 4 - gcd4(S) + 3) / 4 consecutive aligned words starting at (addr & ~3).
+// ---------------------------------------------------------------------------------------------------
+template <int S> struct LoadShape { static constexpr int NRAW = (S + (4 - gcd4(S)) + 3) / 4; };
+
+template <int S, int W> DCB_DEV void align_state(const uint32_t (&raw)[LoadShape<S>::NRAW], uint32_t byte_in_word, uint32_t (&w)[W]) {
+  constexpr int NRAW = LoadShape<S>::NRAW;
+  const uint32_t sh = 8 * byte_in_word;
+#pragma unroll
+  for (int k = 0; k < W; k++) {
+    const uint32_t lo = (k < NRAW) ? raw[(k < NRAW) ? k : 0] : 0u;
+    const uint32_t hi = (k + 1 < NRAW) ? raw[(k + 1 < NRAW) ? k + 1 : 0] : 0u;
+    const uint32_t v = (gcd4(S) == 4) ? lo : __funnelshift_r(lo, hi, sh);
+    w[k] = v & valid_mask<S>(k);
+  }
+}
+
+}  // namespace dcb

@@ -1,0 +1,173 @@
+/* dcb.h -- C ABI of libdcb_b200.so: the B200 (sm_100a) implementation of DeepCubeA's batched
+ * environment step and batched weighted A* (BWAS) node expansion.
+ *
+ * This header is the drop-in boundary.  The reference has no in-process native library for this path:
+ * its native side is a child PROCESS (cpp/parallel_weighted_astar.cpp) driven over argv
+ * (parallel_weighted_astar.cpp:352-356), a positional stdout protocol (search_methods/astar.py:529-532)
+ * and an AF_UNIX request/response socket (parallel_weighted_astar.cpp:121-136, 275-279;
+ * astar.py:571-616).  Each entry point below names the reference code it replaces.  INTEGRATION.md
+ * shows the ctypes binding a maintainer would add to search_methods/astar.py / environments/*.py.
+ *
+ * Conventions
+ *   - plain C types only; every `d_` pointer is a DEVICE pointer owned by the caller (PyTorch in this
+ *     repo), every `h_` pointer is a HOST pointer; the library never frees caller memory.
+ *   - `stream` is a cudaStream_t passed as void*; all device entry points are asynchronous on it and
+ *     touch no global mutable state (move tables are compile-time constants), so they are thread-safe
+ *     per (device, stream).
+ *   - return value: DCB_OK (0) or a negative DCB_ERR_* code.  Nothing throws, exits or prints.
+ *   - layouts: states are packed uint8, `state_bytes` per state, no padding (cube3 54, puzzle15 16,
+ *     puzzle24 25, puzzle35 36, puzzle48 49).  Children of parent p are contiguous, move-minor:
+ *     children[(p*num_moves + a)*state_bytes ...] -- the order of Environment.expand
+ *     (environments/cube3.py:129-161) and of getNextStates (cpp/environments.cpp:236-243).
+ */
+#ifndef DCB_H_
+#define DCB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCB_ABI_VERSION 1
+
+/* ---- status codes ------------------------------------------------------------------------------ */
+#define DCB_OK 0
+#define DCB_ERR_BAD_ENV (-1)      /* unknown env id                                                  */
+#define DCB_ERR_BAD_ARG (-2)      /* null pointer, negative count, bad action, bad capacity          */
+#define DCB_ERR_ALIGN (-3)        /* a pointer that must be 16-byte aligned is not                   */
+#define DCB_ERR_CUDA (-4)         /* a CUDA runtime call failed; see dcb_last_cuda_error()           */
+#define DCB_ERR_NO_DEVICE (-5)    /* no CUDA device / wrong architecture (needs sm_100)              */
+#define DCB_ERR_CAPACITY (-6)     /* arena / closed table / open set would overflow                  */
+
+/* ---- environments (utils/env_utils.py:6-28; cpp main :375-390) --------------------------------- */
+#define DCB_ENV_CUBE3 0
+#define DCB_ENV_PUZZLE15 1
+#define DCB_ENV_PUZZLE24 2
+#define DCB_ENV_PUZZLE35 3
+#define DCB_ENV_PUZZLE48 4
+#define DCB_NUM_ENVS 5
+
+int dcb_abi_version(void);
+const char *dcb_error_string(int code);
+/* cudaGetErrorString of the last CUDA failure seen on the calling thread ("" if none). */
+const char *dcb_last_cuda_error(void);
+
+/* Environment.get_num_moves (cube3.py:87-88, n_puzzle.py:91-92); getNumActions (environments.cpp). */
+int dcb_env_num_moves(int env);
+/* bwas_cpp's state_dim table (astar.py:473-486). */
+int dcb_env_state_bytes(int env);
+/* Goal state (cube3.py:37 arange(54); n_puzzle.py:41 [1..n*n-1,0]).  h_out: state_bytes bytes. */
+int dcb_env_goal_state(int env, uint8_t *h_out);
+/* The move tables the kernels were compiled with, for auditing against the reference's:
+ * cube3: perm[12][54] with child[j] = parent[perm[a][j]] (cube3.py:163-171, environments.h:75-105);
+ * puzzles: swap_zero_idxs[n*n][4] (n_puzzle.py:174-214, environments.cpp:4-46).  h_out: int32. */
+int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems);
+
+/* ---- batched environment step, device buffers --------------------------------------------------- */
+/* Environment.expand + is_solved on every child + state hash, one launch.
+ * Replaces Cube3.expand/_move_np (cube3.py:129-171), NPuzzle.expand/_move_np (n_puzzle.py:136-231),
+ * Cube3::getNextStates/isSolved (environments.cpp:222-256), PuzzleN::getNextStates/isSolved (:92-126)
+ * and the OpenMP child loop of parallel_weighted_astar.cpp:217-230.
+ *   d_parents  [n][S]        d_children [n][A][S] (16-byte aligned)
+ *   d_solved   [n][A] u8 (0/1), may be NULL      d_hash [n][A] u64, may be NULL (16-byte aligned)
+ * Hash: project-defined 64-bit state hash (never 0); the reference's hashes (boost::hash_range,
+ * parallel_weighted_astar.cpp:104-111; CPython bytes hash, cube3.py:17-21) are unobservable. */
+int dcb_expand(int env, const uint8_t *d_parents, int64_t n, uint8_t *d_children, uint8_t *d_solved,
+               uint64_t *d_hash, void *stream);
+
+/* Same, but parents are gathered by node id from a node arena (state of node i at d_arena + i*S) and the
+ * children are appended at d_children (normally d_arena + first_child_id*S).  This is the form the A*
+ * loop uses (parallel_weighted_astar.cpp:217-230 reads popped[i]->env).  d_parent_ids [n] u32. */
+int dcb_expand_indexed(int env, const uint8_t *d_arena, const uint32_t *d_parent_ids, int64_t n,
+                       uint8_t *d_children, uint8_t *d_solved, uint64_t *d_hash, void *stream);
+
+/* Environment.next_state for one action (cube3.py:48-54, n_puzzle.py:46-61; getNextState). */
+int dcb_next_state(int env, const uint8_t *d_states, int64_t n, int action, uint8_t *d_next, void *stream);
+/* Environment.is_solved (cube3.py:71-75, n_puzzle.py:78-82; isSolved). d_solved [n] u8. */
+int dcb_is_solved(int env, const uint8_t *d_states, int64_t n, uint8_t *d_solved, void *stream);
+/* Project-defined state hash of arbitrary states. d_hash [n] u64. */
+int dcb_hash_states(int env, const uint8_t *d_states, int64_t n, uint64_t *d_hash, void *stream);
+/* Environment.state_to_nnet_input (cube3.py:77-85: colors/9; n_puzzle.py:84-89: tiles) and the same
+ * conversion in cpp_listener (astar.py:598-602).  d_out [n][S] u8. */
+int dcb_nnet_input(int env, const uint8_t *d_states, int64_t n, uint8_t *d_out, void *stream);
+
+/* ---- batched environment step, HOST buffers (the call a ctypes/cgo-style binding makes) ----------
+ * Copies h_parents to the device, runs dcb_expand, copies results back, synchronises.  `device` is the
+ * CUDA ordinal.  Scratch device memory is allocated and freed inside the call. */
+int dcb_expand_host(int env, const uint8_t *h_parents, int64_t n, uint8_t *h_children, uint8_t *h_solved,
+                    uint64_t *h_hash, int device);
+int dcb_next_state_host(int env, const uint8_t *h_states, int64_t n, int action, uint8_t *h_next, int device);
+int dcb_is_solved_host(int env, const uint8_t *h_states, int64_t n, uint8_t *h_solved, int device);
+
+/* ---- CLOSED: open-addressing hash table in HBM ---------------------------------------------------
+ * Replaces std::unordered_set<Node*,Hash,NodePointerEq> closed and the serial find / insert /
+ * "depth improved -> re-open" loop of parallel_weighted_astar.cpp:142, 243-265, and Instance.closed_dict /
+ * remove_in_closed of astar.py:55, 78-90.
+ * Table = `capacity` (power of two) 16-byte slots {u64 key, u64 val}; key = state hash (0 = empty),
+ * val = (g << 32) | node_id.  Caller allocates dcb_closed_bytes(capacity) bytes and clears the table
+ * with dcb_closed_clear. */
+int64_t dcb_closed_bytes(int64_t capacity);
+int dcb_closed_clear(void *d_table, int64_t capacity, void *stream);
+/* Insert-or-improve for a batch of m candidate nodes whose states already sit in the arena.
+ *   d_hash [m] u64, d_g [m] u32 (path cost = depth), node id of candidate i = first_id + i.
+ *   d_valid [m] u8 or NULL: candidates with valid==0 are ignored (padding).
+ * Result d_keep[i] = 1 iff candidate i is (a) a state never seen, or (b) a seen state reached with a
+ * STRICTLY smaller g -- exactly the keep rule of :246-261 -- and, among duplicates inside this batch, it is
+ * the one with the smallest (g, id).  Equal hashes are verified by comparing the S state bytes in the
+ * arena; on a true 64-bit collision the candidate is kept (never wrongly dropped).
+ * d_slot [m] u32 is scratch.  Two launches (insert, resolve). */
+int dcb_closed_insert(int env, void *d_table, int64_t capacity, const uint8_t *d_arena,
+                      const uint64_t *d_hash, const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id,
+                      int64_t m, uint32_t *d_slot, uint8_t *d_keep, uint32_t *d_num_entries, void *stream);
+
+/* ---- OPEN: bucket priority queue in HBM ----------------------------------------------------------
+ * Replaces std::priority_queue<Node*,...,compareNodeCost> open (parallel_weighted_astar.cpp:141), the pop
+ * loop :177-204 and the push loop :309-319; heapq open_set of astar.py:53, 64-76.
+ * Storage: flat arrays d_key [cap] u32 (cost as non-negative float bits: order-preserving) and
+ * d_id [cap] u32, plus a persistent 4096-bin histogram over the top 12 key bits (the "buckets").
+ * Ties on cost are broken by smaller node id (the reference's C++ order is unspecified; Python's is
+ * FIFO, which this matches). */
+#define DCB_OPEN_BINS 4096
+typedef struct dcb_open_state {      /* lives in device memory; 16-byte aligned                      */
+  uint32_t size;                     /* live entries in d_key / d_id                                  */
+  uint32_t n_popped;                 /* entries returned by the last pop                              */
+  uint32_t thr_key;                  /* last pop: threshold (key,id) -- everything <= it was popped   */
+  uint32_t thr_id;
+  uint32_t min_key;                  /* last pop: smallest key popped (popped[0]->cost)               */
+  uint32_t goal_id;                  /* best solved node popped so far (0xffffffff = none)            */
+  uint32_t goal_key;
+  uint32_t done;                     /* termination rule of :205-208 fired                            */
+  uint32_t scratch[8];
+} dcb_open_state;
+int64_t dcb_open_hist_bytes(void);   /* DCB_OPEN_BINS * 4                                              */
+int dcb_open_clear(dcb_open_state *d_state, uint32_t *d_hist, void *stream);
+/* Append m entries (cost f32 >= 0, node id); entries with d_keep[i]==0 are skipped (d_keep may be NULL). */
+int dcb_open_push(dcb_open_state *d_state, uint32_t *d_hist, uint32_t *d_key, uint32_t *d_id,
+                  int64_t capacity, const float *d_cost, const uint32_t *d_ids, const uint8_t *d_keep,
+                  int64_t m, void *stream);
+/* Remove the (up to) `batch` smallest entries; with `stop_at_goal` the pop is truncated right after the
+ * cheapest SOLVED entry among them (the `break` at :190-203) and goal bookkeeping / termination
+ * (:196-208) is updated in d_state.  d_node_solved [arena] u8 gives the solved flag per node id.
+ * d_popped_ids [batch] receives the ids (unordered).  d_scratch: dcb_open_scratch_bytes(capacity). */
+int64_t dcb_open_scratch_bytes(int64_t capacity);
+int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_hist, uint32_t *d_key, uint32_t *d_id,
+                 int64_t capacity, int32_t batch, int stop_at_goal, const uint8_t *d_node_solved,
+                 uint32_t *d_popped_ids, void *d_scratch, void *stream);
+
+/* ---- node bookkeeping ---------------------------------------------------------------------------- */
+/* cost = heuristic * (!solved) + weight * g, float32, the expression of parallel_weighted_astar.cpp:298
+ * (and astar.py:196 in float64).  d_h may hold negative values; they are clipped at 0 first
+ * (clip_zero=True, nnet_utils.py:193-194).  Also records g per node. */
+int dcb_compute_cost(const float *d_h, const uint32_t *d_g, const uint8_t *d_solved, float weight,
+                     int64_t m, float *d_cost, void *stream);
+/* Path reconstruction (parallel_weighted_astar.cpp:336-341, astar.py:213-229): follows parent links on
+ * the device.  Node ids: move = id % A, parent = d_slot_parent[id / A].  Writes moves root->goal into
+ * d_moves [max_len] and the length into d_len; length -1 if max_len was too small. */
+int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_id, int32_t max_len,
+                         uint8_t *d_moves, int32_t *d_len, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCB_H_ */

@@ -1,0 +1,200 @@
+"""numpy restatement of the reference's environment step (cube3 / n-puzzle).  TEST INFRASTRUCTURE ONLY.
+
+Pinned against tests/golden/* (generated from the unmodified reference by tests/golden/make_golden.py):
+tables, 10k seeded scrambles x 12 moves (config 1), the 21,349 / 26,011 / 127,835 (s,a,s') triples of the
+shipped results, and the optimal solutions shipped with data/*/test.  `state_hash64` has no reference
+counterpart (reference hashes are CPython's salted bytes-hash / boost::hash_range, both unobservable):
+it is the definition the CUDA path must reproduce bit-exactly -- hash values: parity unpinned by design.
+"""
+from __future__ import annotations
+
+import json
+import os
+import random
+from typing import List, Tuple
+
+import numpy as np
+
+_GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+class OracleCube3:
+    """environments/cube3.py:27-171 and cpp/environments.cpp:222-256."""
+    name = "cube3"
+    state_dim = 54
+    num_moves = 12
+
+    def __init__(self):
+        t = json.load(open(os.path.join(_GOLD, "cube3_tables.json")))
+        self.moves: List[str] = t["moves"]
+        self.moves_rev: List[str] = t["moves_rev"]
+        self.idxs_new = [np.array(x) for x in t["idxs_new"]]   # cube3.py:183-256 / environments.h:91-104
+        self.idxs_old = [np.array(x) for x in t["idxs_old"]]   # environments.h:77-90
+        self.goal = np.arange(54, dtype=np.uint8)               # cube3.py:37
+        self.rev_action = [self.moves_rev.index(m) for m in self.moves]  # cube3.py:56-60
+
+    def move(self, states: np.ndarray, action: int) -> np.ndarray:
+        """cube3.py:163-171 `_move_np`: copy, then next[:, new] = cur[:, old]."""
+        nxt = states.copy()
+        nxt[:, self.idxs_new[action]] = states[:, self.idxs_old[action]]
+        return nxt
+
+    def prev(self, states: np.ndarray, action: int) -> np.ndarray:
+        return self.move(states, self.rev_action[action])
+
+    def is_solved(self, states: np.ndarray) -> np.ndarray:
+        """cube3.py:71-75: sticker identity (state[i] == i), not colour equivalence."""
+        return np.all(states == self.goal[None, :], axis=1)
+
+    def nnet_input(self, states: np.ndarray) -> np.ndarray:
+        """cube3.py:77-85: (colors / 9).astype(uint8) -> colour id 0..5."""
+        return (states / 9).astype(np.uint8)
+
+    def expand(self, states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        """cube3.py:129-161: children[N,12,54] parent-major / move-minor, transition cost 1.0 each."""
+        ch = np.stack([self.move(states, a) for a in range(12)], axis=1)
+        return ch, np.ones((states.shape[0], 12), dtype=np.float64)
+
+    def generate_states(self, n: int, back: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
+        """cube3.py:96-127: same numpy / `random` call sequence, so fixed seeds reproduce the reference."""
+        scrambs = list(range(back[0], back[1] + 1))
+        st = np.repeat(self.goal[None, :].copy(), n, axis=0)
+        scr = np.random.choice(scrambs, n)
+        nb = np.zeros(n)
+        lt = nb < scr
+        while np.any(lt):
+            idxs = np.where(lt)[0]
+            sub = int(max(len(idxs) / 12, 1))
+            idxs = np.random.choice(idxs, sub)
+            mv = random.randrange(12)
+            st[idxs] = self.move(st[idxs], mv)
+            nb[idxs] = nb[idxs] + 1
+            lt[idxs] = nb[idxs] < scr[idxs]
+        return st, scr
+
+
+class OracleNPuzzle:
+    """environments/n_puzzle.py:27-231 and cpp/environments.cpp:4-126."""
+    num_moves = 4
+
+    def __init__(self, dim: int):
+        self.dim = dim
+        self.state_dim = dim * dim
+        self.name = "puzzle%d" % (dim * dim - 1)
+        t = json.load(open(os.path.join(_GOLD, "puzzle_tables.json")))[str(dim)]
+        self.moves, self.moves_rev = t["moves"], t["moves_rev"]
+        self.swap = np.array(t["swap_zero_idxs"], dtype=np.int64)   # n_puzzle.py:174-214
+        self.goal = np.array(t["goal"], dtype=np.uint8)             # n_puzzle.py:41
+        self.rev_action = [self.moves_rev.index(m) for m in self.moves]
+
+    @staticmethod
+    def build_swap_table(dim: int) -> np.ndarray:
+        """Independent restatement of n_puzzle.py:174-214 / environments.cpp:4-46 (checked against golden)."""
+        t = np.zeros((dim * dim, 4), dtype=np.int64)
+        for i in range(dim):
+            for j in range(dim):
+                z = i * dim + j
+                t[z, 0] = (i + 1) * dim + j if i < dim - 1 else z   # U: blank swaps with the tile below
+                t[z, 1] = (i - 1) * dim + j if i > 0 else z         # D
+                t[z, 2] = i * dim + j + 1 if j < dim - 1 else z     # L
+                t[z, 3] = i * dim + j - 1 if j > 0 else z           # R
+        return t
+
+    def move(self, states: np.ndarray, action: int) -> np.ndarray:
+        """n_puzzle.py:216-231: next[z] = cur[swap]; next[swap] = 0 (illegal move => swap == z => no-op)."""
+        nxt = states.copy()
+        rows = np.arange(states.shape[0])
+        z = np.where(states == 0)[1]
+        s = self.swap[z, action]
+        nxt[rows, z] = states[rows, s]
+        nxt[rows, s] = 0
+        return nxt
+
+    def prev(self, states: np.ndarray, action: int) -> np.ndarray:
+        return self.move(states, self.rev_action[action])
+
+    def is_solved(self, states: np.ndarray) -> np.ndarray:
+        """n_puzzle.py:78-82."""
+        return np.all(states == self.goal[None, :], axis=1)
+
+    def nnet_input(self, states: np.ndarray) -> np.ndarray:
+        """n_puzzle.py:84-89: raw tiles."""
+        return states.astype(np.uint8)
+
+    def expand(self, states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        ch = np.stack([self.move(states, a) for a in range(4)], axis=1)
+        return ch, np.ones((states.shape[0], 4), dtype=np.float64)
+
+    def generate_states(self, n: int, back: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
+        """n_puzzle.py:100-134 (same RNG call sequence)."""
+        scrambs = list(range(back[0], back[1] + 1))
+        st = np.repeat(self.goal[None, :].copy(), n, axis=0)
+        scr = np.random.choice(scrambs, n)
+        nb = np.zeros(n)
+        while np.max(nb < scr):
+            idxs = np.where(nb < scr)[0]
+            sub = int(max(len(idxs) / 4, 1))
+            idxs = np.random.choice(idxs, sub)
+            mv = random.randrange(4)
+            st[idxs] = self.move(st[idxs], mv)
+            nb[idxs] = nb[idxs] + 1
+        return st, scr
+
+
+def get_oracle_env(name: str):
+    """utils/env_utils.py:6-28 (cube3 and puzzle(\\d+) only)."""
+    name = name.lower()
+    if name == "cube3":
+        return OracleCube3()
+    if name.startswith("puzzle"):
+        return OracleNPuzzle(int(round((int(name[6:]) + 1) ** 0.5)))
+    raise ValueError("No known environment %s" % name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# State hash (project-defined; see module docstring).  NH-style pair-product universal hash over the
+# state's bytes zero-padded to a multiple of 8, little-endian u32 words, then murmur3's fmix64.
+# ---------------------------------------------------------------------------------------------------
+HASH_SEED = np.uint64(0x9E3779B97F4A7C15)
+
+
+def _splitmix64_keys(n: int) -> np.ndarray:
+    x = 0x0DCB2000DCB200
+    out = []
+    for _ in range(n):
+        x = (x + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        z = z ^ (z >> 31)
+        out.append((z >> 32) | 1)
+    return np.array(out, dtype=np.uint64)
+
+
+HASH_KEYS = _splitmix64_keys(16)   # 32-bit odd keys, enough for states up to 64 bytes
+
+
+def hash_words(state_dim: int) -> int:
+    return 2 * ((state_dim + 7) // 8)
+
+
+def state_hash64(states: np.ndarray) -> np.ndarray:
+    n, s = states.shape
+    w = hash_words(s)
+    buf = np.zeros((n, 4 * w), dtype=np.uint8)
+    buf[:, :s] = states
+    words = buf.view("<u4").astype(np.uint64)                       # [n, w]
+    m = np.uint64(0xFFFFFFFF)
+    acc = np.full(n, HASH_SEED, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        for i in range(0, w, 2):
+            a = (words[:, i] + HASH_KEYS[i]) & m
+            b = (words[:, i + 1] + HASH_KEYS[i + 1]) & m
+            acc = acc + a * b
+        acc ^= acc >> np.uint64(33)
+        acc *= np.uint64(0xFF51AFD7ED558CCD)
+        acc ^= acc >> np.uint64(33)
+        acc *= np.uint64(0xC4CEB9FE1A85EC53)
+        acc ^= acc >> np.uint64(33)
+    acc[acc == 0] = np.uint64(1)                                     # 0 is the closed table's EMPTY key
+    return acc
