@@ -1,0 +1,111 @@
+"""ctypes binding of libdcb_b200.so (the C ABI of include/dcb.h).
+
+There is NO CPU fallback: if the library is missing or a call fails, a DcbError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdcb_b200.so")
+
+ENV_IDS = {"cube3": 0, "puzzle15": 1, "puzzle24": 2, "puzzle35": 3, "puzzle48": 4}
+
+
+class DcbError(RuntimeError):
+    pass
+
+
+class OpenState(ctypes.Structure):
+    """dcb_open_state (include/dcb.h)."""
+    _fields_ = [(n, c_uint32) for n in (
+        "size", "n_popped", "thr_key", "thr_id", "min_key", "goal_id", "goal_key", "done",
+        "overflow", "need", "prefix", "cand_count", "n_holes", "n_surv", "take_all", "n_at_pop")]
+
+
+_lib = None
+
+_P = c_void_p  # every device/host buffer is passed as a raw address
+_SIGS = {
+    "dcb_abi_version": (c_int, []),
+    "dcb_error_string": (c_char_p, [c_int]),
+    "dcb_last_cuda_error": (c_char_p, []),
+    "dcb_env_num_moves": (c_int, [c_int]),
+    "dcb_env_state_bytes": (c_int, [c_int]),
+    "dcb_env_slot_align": (c_int, [c_int]),
+    "dcb_env_goal_state": (c_int, [c_int, _P]),
+    "dcb_env_move_table": (c_int, [c_int, _P, c_int64]),
+    "dcb_expand": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P]),
+    "dcb_expand_indexed": (c_int, [c_int, _P, _P, c_int64, _P, _P, _P, _P]),
+    "dcb_next_state": (c_int, [c_int, _P, c_int64, c_int, _P, _P]),
+    "dcb_is_solved": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "dcb_hash_states": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "dcb_nnet_input": (c_int, [c_int, _P, c_int64, _P, _P]),
+    "dcb_expand_host": (c_int, [c_int, _P, c_int64, _P, _P, _P, c_int]),
+    "dcb_next_state_host": (c_int, [c_int, _P, c_int64, c_int, _P, c_int]),
+    "dcb_is_solved_host": (c_int, [c_int, _P, c_int64, _P, c_int]),
+    "dcb_closed_bytes": (c_int64, [c_int64]),
+    "dcb_closed_clear": (c_int, [_P, c_int64, _P]),
+    "dcb_closed_insert": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P, c_uint32, c_int64, _P, _P, _P, _P]),
+    "dcb_closed_rehash": (c_int, [_P, c_int64, _P, c_int64, _P]),
+    "dcb_open_clear": (c_int, [_P, _P]),
+    "dcb_open_push": (c_int, [_P, _P, _P, c_int64, _P, _P, c_uint32, _P, c_int64, _P]),
+    "dcb_open_scratch_bytes": (c_int64, [c_int64, c_int64]),
+    "dcb_open_pop": (c_int, [_P, _P, _P, c_int64, c_int32, c_int, _P, _P, _P, _P]),
+    "dcb_child_meta": (c_int, [c_int, _P, c_int64, c_uint32, _P, _P, _P]),
+    "dcb_compact_kept": (c_int, [_P, c_uint32, c_int64, _P, _P, _P]),
+    "dcb_gather_nnet_input": (c_int, [c_int, _P, _P, c_int64, _P, _P]),
+    "dcb_compute_cost": (c_int, [_P, _P, _P, _P, c_float, c_int64, _P, _P]),
+    "dcb_reconstruct_path": (c_int, [c_int, _P, c_uint32, c_int32, _P, _P, _P]),
+}
+
+
+def exported_symbols():
+    """Every symbol include/dcb.h declares (used by the CPU-tier ABI test)."""
+    return sorted(_SIGS)
+
+
+def load():
+    """Load the library once; raise DcbError (never fall back) if it is not there."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise DcbError("libdcb_b200.so is not built (%s). Run `python -m deepcubea_b200.build`; "
+                       "there is no CPU fallback for this path." % LIB_PATH)
+    try:
+        import torch  # noqa: F401  (loads the CUDA runtime the library links against)
+    except Exception:  # pragma: no cover
+        pass
+    try:
+        lib = ctypes.CDLL(LIB_PATH)
+    except OSError as e:
+        raise DcbError("cannot load %s: %s" % (LIB_PATH, e))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.dcb_abi_version() != 1:
+        raise DcbError("libdcb_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc == 0:
+        return
+    lib = load()
+    msg = lib.dcb_error_string(rc).decode()
+    cuda = lib.dcb_last_cuda_error().decode()
+    raise DcbError("%s failed: %s (%d)%s" % (what or "dcb call", msg, rc, (" -- CUDA: " + cuda) if cuda else ""))
+
+
+def ptr(t) -> int:
+    """Raw address of a torch tensor / numpy array / None."""
+    if t is None:
+        return None
+    if hasattr(t, "data_ptr"):
+        return t.data_ptr()
+    return t.ctypes.data

@@ -1,0 +1,294 @@
+// api.cu -- the extern "C" surface declared in include/dcb.h: argument validation, error reporting,
+// host-buffer convenience entry points.  No kernel lives here.
+#include <cuda_runtime.h>
+#include <string.h>
+#include "cube3_moves.cuh"
+#include "dcb_internal.h"
+
+namespace dcb {
+static thread_local cudaError_t t_last_cuda = cudaSuccess;
+int dcb_record_cuda(cudaError_t e) {
+  if (e == cudaSuccess) return DCB_OK;
+  t_last_cuda = e;
+  return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? DCB_ERR_NO_DEVICE : DCB_ERR_CUDA;
+}
+int dcb_cuda_fail() { return dcb_record_cuda(cudaGetLastError()); }
+int dcb_check_launch() { return dcb_record_cuda(cudaGetLastError()); }
+
+int closed_clear_device(void *tbl, int64_t cap, cudaStream_t st);
+int closed_insert_device(int env, void *tbl, int64_t cap, const uint8_t *arena, const uint64_t *hash, const uint32_t *g,
+                         const uint8_t *valid, uint32_t first_id, int64_t m, uint32_t *slot, uint8_t *keep,
+                         uint32_t *num_entries, cudaStream_t st);
+int closed_rehash_device(const void *old_tbl, int64_t old_cap, void *new_tbl, int64_t new_cap, cudaStream_t st);
+int open_clear_device(void *state, cudaStream_t st);
+int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
+                     uint32_t first_id, const uint8_t *keep, int64_t m, cudaStream_t st);
+int64_t open_scratch_bytes(int64_t capacity, int64_t batch);
+int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, int32_t batch, int stop_at_goal,
+                    const uint8_t *node_solved, uint32_t *popped_ids, void *scratch, cudaStream_t st);
+int child_meta_device(const uint32_t *parent_ids, int64_t n_parents, int A, uint32_t first_id, uint32_t *node_g,
+                      uint32_t *slot_parent, cudaStream_t st);
+int compact_kept_device(const uint8_t *keep, uint32_t first_id, int64_t m, uint32_t *out_ids, uint32_t *counter, cudaStream_t st);
+int gather_nnet_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t m, uint8_t *out, cudaStream_t st);
+int cost_device(const float *h, const uint32_t *ids, const uint32_t *node_g, const uint8_t *node_solved, float weight,
+                int64_t m, float *cost, cudaStream_t st);
+int path_device(const uint32_t *slot_parent, uint32_t goal_id, int A, int32_t max_len, uint8_t *moves, int32_t *len, cudaStream_t st);
+}  // namespace dcb
+
+using namespace dcb;
+
+namespace {
+const int kStateBytes[DCB_NUM_ENVS] = {54, 16, 25, 36, 49};
+const int kNumMoves[DCB_NUM_ENVS] = {12, 4, 4, 4, 4};
+const int kDim[DCB_NUM_ENVS] = {3, 4, 5, 6, 7};
+inline bool env_ok(int env) { return env >= 0 && env < DCB_NUM_ENVS; }
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+inline bool pow2(int64_t v) { return v > 0 && (v & (v - 1)) == 0; }
+}  // namespace
+
+extern "C" {
+
+int dcb_abi_version(void) { return DCB_ABI_VERSION; }
+
+const char *dcb_error_string(int code) {
+  switch (code) {
+    case DCB_OK: return "ok";
+    case DCB_ERR_BAD_ENV: return "unknown environment id";
+    case DCB_ERR_BAD_ARG: return "bad argument";
+    case DCB_ERR_ALIGN: return "pointer not 16-byte aligned";
+    case DCB_ERR_CUDA: return "CUDA runtime error";
+    case DCB_ERR_NO_DEVICE: return "no usable CUDA device";
+    case DCB_ERR_CAPACITY: return "capacity exceeded";
+  }
+  return "unknown error code";
+}
+const char *dcb_last_cuda_error(void) { return t_last_cuda == cudaSuccess ? "" : cudaGetErrorString(t_last_cuda); }
+
+int dcb_env_num_moves(int env) { return env_ok(env) ? kNumMoves[env] : DCB_ERR_BAD_ENV; }
+int dcb_env_state_bytes(int env) { return env_ok(env) ? kStateBytes[env] : DCB_ERR_BAD_ENV; }
+int dcb_env_slot_align(int env) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  const int rec = kStateBytes[env] * kNumMoves[env];
+  int a = 1;
+  while ((rec * a) % 16) a *= 2;
+  return a;
+}
+int dcb_env_goal_state(int env, uint8_t *h_out) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (!h_out) return DCB_ERR_BAD_ARG;
+  const int s = kStateBytes[env];
+  for (int j = 0; j < s; j++) h_out[j] = env == 0 ? (uint8_t)j : (uint8_t)((j + 1) % s);
+  return DCB_OK;
+}
+int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (!h_out) return DCB_ERR_BAD_ARG;
+  if (env == 0) {
+    if (capacity_elems < 12 * 54) return DCB_ERR_BAD_ARG;
+    for (int a = 0; a < 12; a++)
+      for (int j = 0; j < 54; j++) h_out[a * 54 + j] = kCube3PermHost[a][j];
+    return DCB_OK;
+  }
+  const int d = kDim[env];
+  if (capacity_elems < (int64_t)d * d * 4) return DCB_ERR_BAD_ARG;
+  for (int i = 0; i < d; i++)
+    for (int j = 0; j < d; j++) {
+      const int z = i * d + j;
+      h_out[z * 4 + 0] = i < d - 1 ? z + d : z;   // U: blank swaps with the tile below
+      h_out[z * 4 + 1] = i > 0 ? z - d : z;       // D
+      h_out[z * 4 + 2] = j < d - 1 ? z + 1 : z;   // L
+      h_out[z * 4 + 3] = j > 0 ? z - 1 : z;       // R
+    }
+  return DCB_OK;
+}
+
+int dcb_expand(int env, const uint8_t *d_parents, int64_t n, uint8_t *d_children, uint8_t *d_solved, uint64_t *d_hash,
+               void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!d_parents || !d_children))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_children) || !aligned16(d_hash) || (reinterpret_cast<uintptr_t>(d_parents) & 3u) ||
+      (reinterpret_cast<uintptr_t>(d_solved) & 3u))
+    return DCB_ERR_ALIGN;
+  return expand_device(env, d_parents, nullptr, n, d_children, d_solved, d_hash, S(stream));
+}
+int dcb_expand_indexed(int env, const uint8_t *d_arena, const uint32_t *d_parent_ids, int64_t n, uint8_t *d_children,
+                       uint8_t *d_solved, uint64_t *d_hash, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!d_arena || !d_children || !d_parent_ids))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_children) || !aligned16(d_hash) || (reinterpret_cast<uintptr_t>(d_arena) & 3u) ||
+      (reinterpret_cast<uintptr_t>(d_solved) & 3u))
+    return DCB_ERR_ALIGN;
+  return expand_device(env, d_arena, d_parent_ids, n, d_children, d_solved, d_hash, S(stream));
+}
+int dcb_next_state(int env, const uint8_t *d_states, int64_t n, int action, uint8_t *d_next, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || action < 0 || action >= kNumMoves[env] || (n > 0 && (!d_states || !d_next))) return DCB_ERR_BAD_ARG;
+  if ((reinterpret_cast<uintptr_t>(d_states) & 3u) || (reinterpret_cast<uintptr_t>(d_next) & 3u)) return DCB_ERR_ALIGN;
+  return next_state_device(env, d_states, n, action, d_next, S(stream));
+}
+int dcb_is_solved(int env, const uint8_t *d_states, int64_t n, uint8_t *d_solved, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!d_states || !d_solved))) return DCB_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(d_states) & 3u) return DCB_ERR_ALIGN;
+  return is_solved_device(env, d_states, n, d_solved, S(stream));
+}
+int dcb_hash_states(int env, const uint8_t *d_states, int64_t n, uint64_t *d_hash, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!d_states || !d_hash))) return DCB_ERR_BAD_ARG;
+  if (reinterpret_cast<uintptr_t>(d_states) & 3u) return DCB_ERR_ALIGN;
+  return hash_states_device(env, d_states, n, d_hash, S(stream));
+}
+int dcb_nnet_input(int env, const uint8_t *d_states, int64_t n, uint8_t *d_out, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!d_states || !d_out))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_states) || !aligned16(d_out)) return DCB_ERR_ALIGN;
+  return nnet_input_device(env, d_states, n, d_out, S(stream));
+}
+
+// ---- host-buffer entry points ------------------------------------------------------------------------
+#define DCB_TRY(expr)                                       \
+  do {                                                      \
+    const int rc__ = dcb_record_cuda(expr);                 \
+    if (rc__) { rc = rc__; goto done; }                     \
+  } while (0)
+
+int dcb_expand_host(int env, const uint8_t *h_parents, int64_t n, uint8_t *h_children, uint8_t *h_solved, uint64_t *h_hash,
+                    int device) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!h_parents || !h_children))) return DCB_ERR_BAD_ARG;
+  if (n == 0) return DCB_OK;
+  const int64_t s = kStateBytes[env], a = kNumMoves[env];
+  uint8_t *d_par = nullptr, *d_ch = nullptr, *d_sv = nullptr;
+  uint64_t *d_h = nullptr;
+  cudaStream_t st = nullptr;
+  int rc = DCB_OK;
+  DCB_TRY(cudaSetDevice(device));
+  DCB_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  DCB_TRY(cudaMalloc(&d_par, n * s + 16));
+  DCB_TRY(cudaMalloc(&d_ch, n * a * s + 16));
+  if (h_solved) DCB_TRY(cudaMalloc(&d_sv, n * a + 16));
+  if (h_hash) DCB_TRY(cudaMalloc(&d_h, n * a * 8 + 16));
+  DCB_TRY(cudaMemcpyAsync(d_par, h_parents, n * s, cudaMemcpyHostToDevice, st));
+  rc = expand_device(env, d_par, nullptr, n, d_ch, d_sv, d_h, st);
+  if (rc) goto done;
+  DCB_TRY(cudaMemcpyAsync(h_children, d_ch, n * a * s, cudaMemcpyDeviceToHost, st));
+  if (h_solved) DCB_TRY(cudaMemcpyAsync(h_solved, d_sv, n * a, cudaMemcpyDeviceToHost, st));
+  if (h_hash) DCB_TRY(cudaMemcpyAsync(h_hash, d_h, n * a * 8, cudaMemcpyDeviceToHost, st));
+  DCB_TRY(cudaStreamSynchronize(st));
+done:
+  cudaFree(d_par); cudaFree(d_ch); cudaFree(d_sv); cudaFree(d_h);
+  if (st) cudaStreamDestroy(st);
+  return rc;
+}
+
+int dcb_next_state_host(int env, const uint8_t *h_states, int64_t n, int action, uint8_t *h_next, int device) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || action < 0 || action >= kNumMoves[env] || (n > 0 && (!h_states || !h_next))) return DCB_ERR_BAD_ARG;
+  if (n == 0) return DCB_OK;
+  const int64_t s = kStateBytes[env];
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  int rc = DCB_OK;
+  DCB_TRY(cudaSetDevice(device));
+  DCB_TRY(cudaMalloc(&d_in, n * s + 16));
+  DCB_TRY(cudaMalloc(&d_out, n * s + 16));
+  DCB_TRY(cudaMemcpy(d_in, h_states, n * s, cudaMemcpyHostToDevice));
+  rc = next_state_device(env, d_in, n, action, d_out, nullptr);
+  if (rc) goto done;
+  DCB_TRY(cudaMemcpy(h_next, d_out, n * s, cudaMemcpyDeviceToHost));
+done:
+  cudaFree(d_in); cudaFree(d_out);
+  return rc;
+}
+
+int dcb_is_solved_host(int env, const uint8_t *h_states, int64_t n, uint8_t *h_solved, int device) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n < 0 || (n > 0 && (!h_states || !h_solved))) return DCB_ERR_BAD_ARG;
+  if (n == 0) return DCB_OK;
+  const int64_t s = kStateBytes[env];
+  uint8_t *d_in = nullptr, *d_out = nullptr;
+  int rc = DCB_OK;
+  DCB_TRY(cudaSetDevice(device));
+  DCB_TRY(cudaMalloc(&d_in, n * s + 16));
+  DCB_TRY(cudaMalloc(&d_out, n + 16));
+  DCB_TRY(cudaMemcpy(d_in, h_states, n * s, cudaMemcpyHostToDevice));
+  rc = is_solved_device(env, d_in, n, d_out, nullptr);
+  if (rc) goto done;
+  DCB_TRY(cudaMemcpy(h_solved, d_out, n, cudaMemcpyDeviceToHost));
+done:
+  cudaFree(d_in); cudaFree(d_out);
+  return rc;
+}
+
+// ---- CLOSED ---------------------------------------------------------------------------------------------
+int64_t dcb_closed_bytes(int64_t capacity) { return pow2(capacity) ? capacity * 16 : DCB_ERR_BAD_ARG; }
+int dcb_closed_clear(void *d_table, int64_t capacity, void *stream) {
+  if (!d_table || !pow2(capacity)) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_table)) return DCB_ERR_ALIGN;
+  return closed_clear_device(d_table, capacity, S(stream));
+}
+int dcb_closed_insert(int env, void *d_table, int64_t capacity, const uint8_t *d_arena, const uint64_t *d_hash,
+                      const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id, int64_t m, uint32_t *d_slot,
+                      uint8_t *d_keep, uint32_t *d_num_entries, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (m < 0 || !pow2(capacity) || capacity > (int64_t(1) << 32) || (m > 0 && (!d_table || !d_arena || !d_hash || !d_g || !d_slot || !d_keep)))
+    return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_table) || (reinterpret_cast<uintptr_t>(d_arena) & 3u)) return DCB_ERR_ALIGN;
+  return closed_insert_device(env, d_table, capacity, d_arena, d_hash, d_g, d_valid, first_id, m, d_slot, d_keep, d_num_entries,
+                              S(stream));
+}
+int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int64_t new_capacity, void *stream) {
+  if (!d_old || !d_new || !pow2(old_capacity) || !pow2(new_capacity)) return DCB_ERR_BAD_ARG;
+  return closed_rehash_device(d_old, old_capacity, d_new, new_capacity, S(stream));
+}
+
+// ---- OPEN ------------------------------------------------------------------------------------------------
+int dcb_open_clear(dcb_open_state *d_state, void *stream) {
+  if (!d_state) return DCB_ERR_BAD_ARG;
+  return open_clear_device(d_state, S(stream));
+}
+int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, const float *d_cost,
+                  const uint32_t *d_ids, uint32_t first_id, const uint8_t *d_keep, int64_t m, void *stream) {
+  if (m < 0 || capacity <= 0 || capacity > 0xFFFFFFFFll || (m > 0 && (!d_state || !d_key || !d_id || !d_cost))) return DCB_ERR_BAD_ARG;
+  return open_push_device(d_state, d_key, d_id, capacity, d_cost, d_ids, first_id, d_keep, m, S(stream));
+}
+int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch) {
+  return (capacity > 0 && batch > 0) ? open_scratch_bytes(capacity, batch) : DCB_ERR_BAD_ARG;
+}
+int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, int32_t batch, int stop_at_goal,
+                 const uint8_t *d_node_solved, uint32_t *d_popped_ids, void *d_scratch, void *stream) {
+  if (!d_state || !d_key || !d_id || !d_popped_ids || !d_scratch || batch <= 0 || capacity <= 0) return DCB_ERR_BAD_ARG;
+  if (stop_at_goal && !d_node_solved) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_scratch)) return DCB_ERR_ALIGN;
+  return open_pop_device(d_state, d_key, d_id, capacity, batch, stop_at_goal, d_node_solved, d_popped_ids, d_scratch, S(stream));
+}
+
+// ---- node bookkeeping --------------------------------------------------------------------------------------
+int dcb_child_meta(int env, const uint32_t *d_parent_ids, int64_t n_parents, uint32_t first_id, uint32_t *d_node_g,
+                   uint32_t *d_slot_parent, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (n_parents < 0 || first_id % kNumMoves[env] || (n_parents > 0 && (!d_parent_ids || !d_node_g || !d_slot_parent))) return DCB_ERR_BAD_ARG;
+  return child_meta_device(d_parent_ids, n_parents, kNumMoves[env], first_id, d_node_g, d_slot_parent, S(stream));
+}
+int dcb_compact_kept(const uint8_t *d_keep, uint32_t first_id, int64_t m, uint32_t *d_out_ids, uint32_t *d_counter, void *stream) {
+  if (m < 0 || (m > 0 && (!d_keep || !d_out_ids || !d_counter))) return DCB_ERR_BAD_ARG;
+  return compact_kept_device(d_keep, first_id, m, d_out_ids, d_counter, S(stream));
+}
+int dcb_gather_nnet_input(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, uint8_t *d_out, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (m < 0 || (m > 0 && (!d_arena || !d_ids || !d_out))) return DCB_ERR_BAD_ARG;
+  return gather_nnet_device(env, d_arena, d_ids, m, d_out, S(stream));
+}
+int dcb_compute_cost(const float *d_h, const uint32_t *d_ids, const uint32_t *d_node_g, const uint8_t *d_node_solved,
+                     float weight, int64_t m, float *d_cost, void *stream) {
+  if (m < 0 || (m > 0 && (!d_h || !d_ids || !d_node_g || !d_node_solved || !d_cost))) return DCB_ERR_BAD_ARG;
+  return cost_device(d_h, d_ids, d_node_g, d_node_solved, weight, m, d_cost, S(stream));
+}
+int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_id, int32_t max_len, uint8_t *d_moves,
+                         int32_t *d_len, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  if (!d_slot_parent || !d_moves || !d_len || max_len <= 0) return DCB_ERR_BAD_ARG;
+  return path_device(d_slot_parent, goal_id, kNumMoves[env], max_len, d_moves, d_len, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,283 @@
+// expand_kernels.cu -- the batched environment step on sm_100a.
+//
+// expand_kernel<ENV, INDEXED>: one lane owns one parent.  The parent's S bytes are pulled into registers
+// with aligned 32-bit loads (+ funnel shift for the env's natural misalignment), all A children are
+// produced in registers (cube3: PRMT networks; n-puzzle: SIMD-within-register blank swap), hashed
+// (IMAD.WIDE pair products) and solved-checked, and the lane's A*S-byte child record is written to a
+// per-warp shared-memory staging tile.  A 32-parent tile of records is contiguous in the output, so one
+// elected lane ships it with a single TMA bulk store (cp.async.bulk shared->global); the warp only
+// waits for the TMA engine to finish READING the tile before refilling it.  HBM traffic is therefore
+// the algorithmic minimum: S bytes read per parent, A*S + A + 8A bytes written.
+//
+// Replaces Cube3::getNextStates/isSolved, PuzzleN::getNextStates/isSolved (cpp/environments.cpp:92-126,
+// 222-256), the OpenMP loop of parallel_weighted_astar.cpp:217-230, and Environment.expand/_move_np/
+// is_solved of environments/cube3.py:71-75,129-171 and environments/n_puzzle.py:78-82,136-231.
+#include <cuda_runtime.h>
+#include "dcb_internal.h"
+#include "expand_core.cuh"
+#include "ptx.cuh"
+
+namespace dcb {
+
+constexpr int kExpandWarps = 4;
+constexpr int kExpandThreads = kExpandWarps * 32;
+
+// ---- vector stores of a run of record words into the lane's staging slot --------------------------
+template <int K0, int I, int N, int ALIGNW> struct StoreWords {
+  static __device__ __forceinline__ void run(uint32_t *base, const uint32_t (&r)[N]) {
+    if constexpr (I < N) {
+      constexpr int k = K0 + I;
+      if constexpr (ALIGNW >= 4 && k % 4 == 0 && I + 4 <= N) {
+        sts128(base + k, r[I], r[I + 1], r[I + 2], r[I + 3]);
+        StoreWords<K0, I + 4, N, ALIGNW>::run(base, r);
+      } else if constexpr (ALIGNW >= 2 && k % 2 == 0 && I + 2 <= N) {
+        sts64(base + k, r[I], r[I + 1]);
+        StoreWords<K0, I + 2, N, ALIGNW>::run(base, r);
+      } else {
+        sts32(base + k, r[I]);
+        StoreWords<K0, I + 1, N, ALIGNW>::run(base, r);
+      }
+    }
+  }
+};
+
+template <int ENV> struct SmemSink {
+  using Sh = ExpandShape<ENV>;
+  // widest store the lane stride (REC_WORDS) keeps aligned; cube3: 162 words -> 8-byte stores, which are
+  // bank-conflict free at that stride (162 = 2 mod 32: a half-warp's 64-bit stores tile all 32 banks)
+  static constexpr int ALIGNW = (Sh::REC_WORDS % 4 == 0) ? 4 : ((Sh::REC_WORDS % 2 == 0) ? 2 : 1);
+  uint32_t *rec;
+  uint64_t *hash_out;   // this parent's A hashes (16-byte aligned) or nullptr
+  uint32_t *solved_out; // this parent's A flags as words or nullptr
+  uint64_t h_even;
+  uint32_t s_word;
+
+  template <int K0, int N> __device__ __forceinline__ void store_record_words(const uint32_t (&r)[N]) {
+    StoreWords<K0, 0, N, ALIGNW>::run(rec, r);
+  }
+  template <int MOVE> __device__ __forceinline__ void store_hash(uint64_t h) {
+    if constexpr (MOVE % 2 == 0) h_even = h;
+    else if (hash_out) stg_cs_v2u64(hash_out + MOVE - 1, h_even, h);
+  }
+  template <int MOVE> __device__ __forceinline__ void store_solved(bool s) {
+    if constexpr (MOVE % 4 == 0) s_word = 0;
+    s_word |= (s ? 1u : 0u) << (8 * (MOVE % 4));
+    if constexpr (MOVE % 4 == 3) {
+      if (solved_out) stg_cs_u32(solved_out + MOVE / 4, s_word);
+    }
+  }
+};
+
+template <int S> __device__ __forceinline__ void load_raw(const uint8_t *base, uint64_t byte_off, uint32_t (&raw)[LoadShape<S>::NRAW]) {
+  const uint32_t *a = reinterpret_cast<const uint32_t *>(base + (byte_off & ~uint64_t(3)));
+#pragma unroll
+  for (int k = 0; k < LoadShape<S>::NRAW; k++) raw[k] = ldg_nc_u32(a + k);
+}
+
+template <int ENV, bool INDEXED>
+__global__ void __launch_bounds__(kExpandThreads)
+expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids, int64_t n,
+              uint8_t *__restrict__ children, uint8_t *__restrict__ solved, uint64_t *__restrict__ hash) {
+  using Sh = ExpandShape<ENV>;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kTileBytes = 32 * Sh::REC_BYTES;
+  uint8_t *tile_smem = smem_raw + warp * kTileBytes;
+  uint32_t *lane_rec = reinterpret_cast<uint32_t *>(tile_smem) + lane * Sh::REC_WORDS;
+
+  const int64_t n_tiles = (n + 31) >> 5;
+  const int64_t warp_stride = (int64_t)gridDim.x * kExpandWarps;
+  for (int64_t tile = (int64_t)blockIdx.x * kExpandWarps + warp; tile < n_tiles; tile += warp_stride) {
+    const int64_t p = tile * 32 + lane;
+    const bool valid = p < n;
+    // issue the parent loads before waiting on the previous tile's store: they do not touch smem
+    uint32_t raw[LoadShape<Sh::S>::NRAW];
+    uint64_t off = 0;
+    if (valid) {
+      const uint64_t node = INDEXED ? (uint64_t)ids[p] : (uint64_t)p;
+      off = node * Sh::S;
+      load_raw<Sh::S>(src, off, raw);
+    }
+    if (lane == 0) bulk_wait_read_all();   // previous bulk store has drained this warp's staging tile
+    __syncwarp();
+    if (valid) {
+      uint32_t w[Sh::W];
+      align_state<Sh::S, Sh::W>(raw, (uint32_t)(off & 3), w);
+      SmemSink<ENV> sink;
+      sink.rec = lane_rec;
+      sink.hash_out = hash ? hash + p * Sh::A : nullptr;
+      sink.solved_out = solved ? reinterpret_cast<uint32_t *>(solved + p * Sh::A) : nullptr;
+      expand_parent<ENV>(w, sink);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    const int64_t rem = n - tile * 32;
+    const uint32_t bytes = (uint32_t)((rem < 32 ? rem : 32) * Sh::REC_BYTES);
+    const uint32_t bulk = bytes & ~15u;
+    uint8_t *gdst = children + tile * (int64_t)kTileBytes;
+    if (lane == 0 && bulk) {
+      bulk_store_s2g(gdst, tile_smem, bulk);
+      bulk_commit();
+    }
+    // a partial last tile can leave 4..12 trailing bytes that are not a 16-byte multiple
+    if (lane < ((bytes - bulk) >> 2))
+      reinterpret_cast<uint32_t *>(gdst + bulk)[lane] = reinterpret_cast<const uint32_t *>(tile_smem + bulk)[lane];
+  }
+  if (lane == 0) bulk_wait_read_all();
+}
+
+// ---- secondary single-state kernels (Environment.next_state / is_solved / hash / nnet input) -------
+template <int ENV, int MODE>   // MODE 0: next_state, 1: is_solved, 2: hash
+__global__ void __launch_bounds__(256) state_kernel(const uint8_t *__restrict__ states, int64_t n, int action,
+                                                    uint8_t *__restrict__ out_states, uint8_t *__restrict__ out_flag,
+                                                    uint64_t *__restrict__ out_hash) {
+  using Sh = ExpandShape<ENV>;
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    uint32_t raw[LoadShape<Sh::S>::NRAW], w[Sh::W];
+    const uint64_t off = (uint64_t)p * Sh::S;
+    load_raw<Sh::S>(states, off, raw);
+    align_state<Sh::S, Sh::W>(raw, (uint32_t)(off & 3), w);
+    if (MODE == 1) {
+      out_flag[p] = is_goal<ENV, Sh::W>(w) ? 1 : 0;
+    } else if (MODE == 2) {
+      out_hash[p] = state_hash<Sh::W>(w);
+    } else {
+      uint32_t zm[Sh::W], c[Sh::W];
+      if constexpr (EnvTraits<ENV>::kPuzzle) puzzle_blank_mask<EnvTraits<ENV>::DIM, Sh::W>(w, zm);
+      else {
+#pragma unroll
+        for (int i = 0; i < Sh::W; i++) zm[i] = 0;
+      }
+#pragma unroll
+      for (int i = 0; i < Sh::W; i++) c[i] = w[i];
+      ApplyAction<ENV, 0>::run(action, w, zm, c);
+      uint8_t *o = out_states + off;
+      if constexpr (Sh::S % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < Sh::S / 4; k++) reinterpret_cast<uint32_t *>(o)[k] = c[k];
+      } else if constexpr (Sh::S % 2 == 0) {
+#pragma unroll
+        for (int k = 0; k < Sh::S / 2; k++) reinterpret_cast<uint16_t *>(o)[k] = (uint16_t)(c[k / 2] >> (16 * (k % 2)));
+      } else {
+#pragma unroll
+        for (int k = 0; k < Sh::S; k++) o[k] = (uint8_t)(c[k / 4] >> (8 * (k % 4)));
+      }
+    }
+  }
+}
+
+// nnet input: cube3 sticker id / 9 -> colour id (cube3.py:77-85); puzzles: identity (n_puzzle.py:84-89)
+template <bool DIV9> __global__ void __launch_bounds__(256) nnet_input_kernel(const uint8_t *__restrict__ in, int64_t nbytes, uint8_t *__restrict__ out) {
+  const int64_t nvec = nbytes >> 4;
+  const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, ts = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = t0; i < nvec; i += ts) {
+    uint4 v = reinterpret_cast<const uint4 *>(in)[i];
+    if (DIV9) {
+      uint32_t *x = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        uint32_t r = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) r |= ((((x[k] >> (8 * b)) & 0xFF) * 57u) >> 9) << (8 * b);   // floor(v/9), v < 64
+        x[k] = r;
+      }
+    }
+    reinterpret_cast<uint4 *>(out)[i] = v;
+  }
+  for (int64_t i = (nvec << 4) + t0; i < nbytes; i += ts) out[i] = DIV9 ? (uint8_t)((in[i] * 57u) >> 9) : in[i];
+}
+
+// ---- launchers -------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0, v = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    g_num_sms = v > 0 ? v : 148;
+  }
+  return g_num_sms;
+}
+
+template <int ENV, bool INDEXED>
+static int launch_expand(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
+                         uint64_t *hash, cudaStream_t st) {
+  using Sh = ExpandShape<ENV>;
+  if (n == 0) return DCB_OK;
+  constexpr int smem = kExpandWarps * 32 * Sh::REC_BYTES;
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  auto kern = expand_kernel<ENV, INDEXED>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return dcb_cuda_fail();
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kExpandThreads, smem) != cudaSuccess) return dcb_cuda_fail();
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    configured = true;
+  }
+  const int64_t n_tiles = (n + 31) / 32;
+  int64_t blocks = (n_tiles + kExpandWarps - 1) / kExpandWarps;
+  const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  kern<<<(unsigned)blocks, kExpandThreads, smem, st>>>(src, ids, n, children, solved, hash);
+  return dcb_check_launch();
+}
+
+template <bool INDEXED>
+static int dispatch_expand(int env, const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
+                           uint64_t *hash, cudaStream_t st) {
+  switch (env) {
+    case 0: return launch_expand<0, INDEXED>(src, ids, n, children, solved, hash, st);
+    case 1: return launch_expand<1, INDEXED>(src, ids, n, children, solved, hash, st);
+    case 2: return launch_expand<2, INDEXED>(src, ids, n, children, solved, hash, st);
+    case 3: return launch_expand<3, INDEXED>(src, ids, n, children, solved, hash, st);
+    case 4: return launch_expand<4, INDEXED>(src, ids, n, children, solved, hash, st);
+  }
+  return DCB_ERR_BAD_ENV;
+}
+
+int expand_device(int env, const uint8_t *parents, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
+                  uint64_t *hash, cudaStream_t st) {
+  return ids ? dispatch_expand<true>(env, parents, ids, n, children, solved, hash, st)
+             : dispatch_expand<false>(env, parents, nullptr, n, children, solved, hash, st);
+}
+
+template <int MODE>
+static int dispatch_state(int env, const uint8_t *states, int64_t n, int action, uint8_t *out_states, uint8_t *out_flag,
+                          uint64_t *out_hash, cudaStream_t st) {
+  if (n == 0) return DCB_OK;
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  switch (env) {
+    case 0: state_kernel<0, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 1: state_kernel<1, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 2: state_kernel<2, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 3: state_kernel<3, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 4: state_kernel<4, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    default: return DCB_ERR_BAD_ENV;
+  }
+  return dcb_check_launch();
+}
+
+int next_state_device(int env, const uint8_t *states, int64_t n, int action, uint8_t *out, cudaStream_t st) {
+  return dispatch_state<0>(env, states, n, action, out, nullptr, nullptr, st);
+}
+int is_solved_device(int env, const uint8_t *states, int64_t n, uint8_t *out, cudaStream_t st) {
+  return dispatch_state<1>(env, states, n, 0, nullptr, out, nullptr, st);
+}
+int hash_states_device(int env, const uint8_t *states, int64_t n, uint64_t *out, cudaStream_t st) {
+  return dispatch_state<2>(env, states, n, 0, nullptr, nullptr, out, st);
+}
+int nnet_input_device(int env, const uint8_t *states, int64_t n, uint8_t *out, cudaStream_t st) {
+  if (env < 0 || env >= DCB_NUM_ENVS) return DCB_ERR_BAD_ENV;
+  if (n == 0) return DCB_OK;
+  const int64_t nbytes = n * dcb_env_state_bytes(env);
+  int64_t blocks = ((nbytes >> 4) + 255) / 256 + 1;
+  const int64_t cap = (int64_t)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  if (env == 0) nnet_input_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
+  else nnet_input_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
+  return dcb_check_launch();
+}
+
+}  // namespace dcb

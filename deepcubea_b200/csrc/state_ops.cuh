@@ -18,8 +18,8 @@ template <> struct EnvTraits<2> { static constexpr int S = 25, A = 4, DIM = 5; s
 template <> struct EnvTraits<3> { static constexpr int S = 36, A = 4, DIM = 6; static constexpr bool kPuzzle = true; };
 template <> struct EnvTraits<4> { static constexpr int S = 49, A = 4, DIM = 7; static constexpr bool kPuzzle = true; };
 
-constexpr int hash_words(int s) { return 2 * ((s + 7) / 8); }
-constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) ? 2 : 1); }
+DCB_HOSTDEV constexpr int hash_words(int s) { return 2 * ((s + 7) / 8); }
+DCB_HOSTDEV constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) ? 2 : 1); }
 
 // ---------------------------------------------------------------------------------------------------
 // Hash: NH pair-product universal hash (keys from splitmix64, see oracle/oracle_env.py) + murmur3 fmix64.

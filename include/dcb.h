@@ -28,6 +28,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
 
 #define DCB_ABI_VERSION 1
 
@@ -120,53 +123,73 @@ int dcb_closed_clear(void *d_table, int64_t capacity, void *stream);
 int dcb_closed_insert(int env, void *d_table, int64_t capacity, const uint8_t *d_arena,
                       const uint64_t *d_hash, const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id,
                       int64_t m, uint32_t *d_slot, uint8_t *d_keep, uint32_t *d_num_entries, void *stream);
+/* Re-insert every entry of an old table into a (larger, cleared) new one. */
+int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int64_t new_capacity, void *stream);
 
 /* ---- OPEN: bucket priority queue in HBM ----------------------------------------------------------
  * Replaces std::priority_queue<Node*,...,compareNodeCost> open (parallel_weighted_astar.cpp:141), the pop
- * loop :177-204 and the push loop :309-319; heapq open_set of astar.py:53, 64-76.
- * Storage: flat arrays d_key [cap] u32 (cost as non-negative float bits: order-preserving) and
- * d_id [cap] u32, plus a persistent 4096-bin histogram over the top 12 key bits (the "buckets").
- * Ties on cost are broken by smaller node id (the reference's C++ order is unspecified; Python's is
- * FIFO, which this matches). */
-#define DCB_OPEN_BINS 4096
-typedef struct dcb_open_state {      /* lives in device memory; 16-byte aligned                      */
-  uint32_t size;                     /* live entries in d_key / d_id                                  */
-  uint32_t n_popped;                 /* entries returned by the last pop                              */
-  uint32_t thr_key;                  /* last pop: threshold (key,id) -- everything <= it was popped   */
-  uint32_t thr_id;
-  uint32_t min_key;                  /* last pop: smallest key popped (popped[0]->cost)               */
-  uint32_t goal_id;                  /* best solved node popped so far (0xffffffff = none)            */
+ * loop :177-208 and the push loop :309-319; heapq open_set of astar.py:53, 64-76.
+ * Storage: flat unsorted arrays d_key [capacity] u32 (cost as non-negative float bits: order-preserving)
+ * and d_id [capacity] u32.  A pop is an exact radix select of the `batch` smallest (key,id) composites:
+ * two 4096-bucket histogram passes over key bits 31..20 / 19..8, a single-block finish on the boundary
+ * bucket, one partition pass.  Ties on cost break towards the smaller node id (the reference's C++ heap
+ * order is unspecified; Python's heapq is FIFO, which this matches). */
+typedef struct dcb_open_state {      /* lives in device memory; the host may copy it back to inspect     */
+  uint32_t size;                     /* live entries in d_key / d_id                                      */
+  uint32_t n_popped;                 /* entries returned by the last pop                                  */
+  uint32_t thr_key, thr_id;          /* last pop: select threshold (everything <= it was removed)         */
+  uint32_t min_key;                  /* last pop: smallest key popped == popped[0]->cost                  */
+  uint32_t goal_id;                  /* cheapest solved node popped so far (0xffffffff = none)            */
   uint32_t goal_key;
-  uint32_t done;                     /* termination rule of :205-208 fired                            */
-  uint32_t scratch[8];
+  uint32_t done;                     /* 1: termination rule of :205-208 (or :191-193) fired; 2: OPEN empty */
+  uint32_t overflow;                 /* a push ran past `capacity`                                         */
+  uint32_t need, prefix, cand_count, n_holes, n_surv, take_all, n_at_pop;   /* pop-internal              */
 } dcb_open_state;
-int64_t dcb_open_hist_bytes(void);   /* DCB_OPEN_BINS * 4                                              */
-int dcb_open_clear(dcb_open_state *d_state, uint32_t *d_hist, void *stream);
-/* Append m entries (cost f32 >= 0, node id); entries with d_keep[i]==0 are skipped (d_keep may be NULL). */
-int dcb_open_push(dcb_open_state *d_state, uint32_t *d_hist, uint32_t *d_key, uint32_t *d_id,
-                  int64_t capacity, const float *d_cost, const uint32_t *d_ids, const uint8_t *d_keep,
+int dcb_open_clear(dcb_open_state *d_state, void *stream);
+/* Append m entries with cost d_cost[i] (float32 >= 0) and node id (d_ids ? d_ids[i] : first_id + i);
+ * entries with d_keep[i]==0 are skipped (d_keep may be NULL). */
+int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity,
+                  const float *d_cost, const uint32_t *d_ids, uint32_t first_id, const uint8_t *d_keep,
                   int64_t m, void *stream);
-/* Remove the (up to) `batch` smallest entries; with `stop_at_goal` the pop is truncated right after the
- * cheapest SOLVED entry among them (the `break` at :190-203) and goal bookkeeping / termination
- * (:196-208) is updated in d_state.  d_node_solved [arena] u8 gives the solved flag per node id.
- * d_popped_ids [batch] receives the ids (unordered).  d_scratch: dcb_open_scratch_bytes(capacity). */
-int64_t dcb_open_scratch_bytes(int64_t capacity);
-int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_hist, uint32_t *d_key, uint32_t *d_id,
-                 int64_t capacity, int32_t batch, int stop_at_goal, const uint8_t *d_node_solved,
-                 uint32_t *d_popped_ids, void *d_scratch, void *stream);
+/* Remove the (up to) `batch` cheapest entries and write their node ids, in cost order, to d_popped_ids
+ * [batch]; d_state->n_popped says how many.  With `stop_at_goal` the pop is truncated right after the
+ * first SOLVED entry in cost order (the `break` at :190-203; the entries behind it go back to OPEN) and the
+ * goal bookkeeping / termination rule of :186-208 is applied to d_state (goal_id, goal_key, done).
+ * d_node_solved [node id] u8.  d_scratch: dcb_open_scratch_bytes(capacity, batch) bytes, 16-byte aligned. */
+int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch);
+int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, int32_t batch,
+                 int stop_at_goal, const uint8_t *d_node_solved, uint32_t *d_popped_ids, void *d_scratch,
+                 void *stream);
 
-/* ---- node bookkeeping ---------------------------------------------------------------------------- */
-/* cost = heuristic * (!solved) + weight * g, float32, the expression of parallel_weighted_astar.cpp:298
- * (and astar.py:196 in float64).  d_h may hold negative values; they are clipped at 0 first
- * (clip_zero=True, nnet_utils.py:193-194).  Also records g per node. */
-int dcb_compute_cost(const float *d_h, const uint32_t *d_g, const uint8_t *d_solved, float weight,
-                     int64_t m, float *d_cost, void *stream);
-/* Path reconstruction (parallel_weighted_astar.cpp:336-341, astar.py:213-229): follows parent links on
- * the device.  Node ids: move = id % A, parent = d_slot_parent[id / A].  Writes moves root->goal into
- * d_moves [max_len] and the length into d_len; length -1 if max_len was too small. */
+/* ---- node bookkeeping ----------------------------------------------------------------------------
+ * Node ids: id = slot * A + move, state at d_arena + id * S.  Slot 0 holds the root (id 0); each batch of
+ * popped parents gets consecutive slots starting at a multiple of dcb_env_slot_align(env), so that its
+ * child block starts 16-byte aligned for the TMA store of dcb_expand_indexed. */
+int dcb_env_slot_align(int env);
+/* Node{depth,parent} of parallel_weighted_astar.cpp:80-86, 219-226: for child i (0 <= i < n_parents*A) of
+ * popped parent d_parent_ids[i/A]:  d_node_g[first_id+i] = d_node_g[parent] + 1, and per slot
+ * d_slot_parent[(first_id+i)/A] = parent.  first_id must be a multiple of A. */
+int dcb_child_meta(int env, const uint32_t *d_parent_ids, int64_t n_parents, uint32_t first_id,
+                   uint32_t *d_node_g, uint32_t *d_slot_parent, void *stream);
+/* nodesToAdd of :244-262: ids (first_id + i) of the candidates with d_keep[i] != 0, appended (unordered) to
+ * d_out_ids; *d_counter (must be zeroed by the caller) receives the count. */
+int dcb_compact_kept(const uint8_t *d_keep, uint32_t first_id, int64_t m, uint32_t *d_out_ids,
+                     uint32_t *d_counter, void *stream);
+/* state_to_nnet_input of the listed nodes (cube3.py:77-85 / astar.py:598-602): d_out [m][S] u8. */
+int dcb_gather_nnet_input(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m,
+                          uint8_t *d_out, void *stream);
+/* cost = max(h,0) * (!solved) + weight * g in float32 without FMA contraction -- the expression of
+ * parallel_weighted_astar.cpp:298 (astar.py:196 in float64); clip at 0 is nnet_utils.py:193-194. */
+int dcb_compute_cost(const float *d_h, const uint32_t *d_ids, const uint32_t *d_node_g,
+                     const uint8_t *d_node_solved, float weight, int64_t m, float *d_cost, void *stream);
+/* Path reconstruction (parallel_weighted_astar.cpp:336-341, astar.py:213-229) on the device: writes the
+ * moves root->goal into d_moves [max_len] and the length into d_len (-1 if max_len was too small). */
 int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_id, int32_t max_len,
                          uint8_t *d_moves, int32_t *d_len, void *stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif
