@@ -1,0 +1,286 @@
+"""Batch weighted A* search: the reference's Search API and CLI (search_methods/astar.py) on the B200 engine.
+
+API kept: `Node`, `AStar(states, env, heuristic_fn, weights)`, `.step(heuristic_fn, batch_size, include_solved,
+verbose)`, `.has_found_goal()`, `.get_goal_nodes(i)`, `.get_goal_node_smallest_path_cost(i)`,
+`.get_num_nodes_generated(i)`, `.get_popped_nodes()`, module-level `get_path(node)` (astar.py:18-44, 213-340).
+Nodes are views over the device-resident search: OPEN, CLOSED and the node arena never leave HBM; `Node`
+objects are only materialised for goal / popped nodes when asked for.
+
+CLI kept (astar.py:343-397): --states --model_dir --env --batch_size --weight --language --results_dir
+--start_idx --nnet_batch_size --verbose --debug; writes <results_dir>/output.txt and results.pkl with keys
+states, solutions, paths, times, num_nodes_generated.  --language values:
+    cuda (default), cpp : GPU engine with the C++ program's semantics (cpp/parallel_weighted_astar.cpp:138-346),
+                          the variant that produced the reference's shipped results;
+    python              : GPU engine with the Python AStar semantics (astar.py:232-340, 400-454).
+Extra flags: --nnet_precision {fp32,tf32,bf16}, --max_nodes N.
+"""
+from __future__ import annotations
+
+import os
+import pickle
+import sys
+import time
+from argparse import ArgumentParser
+from typing import Any, Callable, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+
+from ..environments.environment_abstract import Environment, State
+from ..search.bwas_gpu import NONE, BWASGpu
+from ..utils import data_utils, env_utils, misc_utils, nnet_utils, search_utils  # noqa: F401
+
+
+class Node:
+    __slots__ = ["state", "path_cost", "heuristic", "cost", "is_solved", "parent_move", "parent", "transition_costs",
+                 "children", "bellman"]
+
+    def __init__(self, state: State, path_cost: float, is_solved: bool, parent_move: Optional[int], parent):
+        self.state: State = state
+        self.path_cost: float = path_cost
+        self.heuristic: Optional[float] = None
+        self.cost: Optional[float] = None
+        self.is_solved: bool = is_solved
+        self.parent_move: Optional[int] = parent_move
+        self.parent: Optional[Node] = parent
+        self.transition_costs: List[float] = []
+        self.children: List[Node] = []
+        self.bellman: float = np.inf
+
+
+def get_path(node: Node) -> Tuple[List[State], List[int], float]:
+    """Walk parent links back to the root (astar.py:213-229)."""
+    path: List[State] = []
+    moves: List[int] = []
+    cur = node
+    while cur.parent is not None:
+        path.append(cur.state)
+        moves.append(cur.parent_move)
+        cur = cur.parent
+    path.append(cur.state)
+    return path[::-1], moves[::-1], node.path_cost
+
+
+def _device_heuristic(heuristic_fn: Callable, env: Environment) -> Callable[[torch.Tensor], torch.Tensor]:
+    """Zero-copy form when the heuristic came from nnet_utils; otherwise adapt a reference-style callable
+    (nnet-format numpy in, numpy out) -- functional for any user heuristic, at PCIe speed."""
+    dev_fn = getattr(heuristic_fn, "device_fn", None)
+    if dev_fn is not None:
+        return dev_fn
+
+    def adapted(x: torch.Tensor) -> torch.Tensor:
+        out = heuristic_fn([x.cpu().numpy()], is_nnet_format=True)
+        return torch.as_tensor(np.asarray(out, dtype=np.float32), device=x.device)
+    return adapted
+
+
+def _env_name(env: Environment) -> str:
+    return "cube3" if type(env).__name__ == "Cube3" else "puzzle%d" % (env.dim * env.dim - 1)
+
+
+class Instance:
+    """One search problem = one device-resident engine (astar.py:50-90 keeps heap + dict per instance)."""
+
+    def __init__(self, env: Environment, state: State, heuristic_fn: Callable, weight: float, max_nodes: int):
+        self.env = env
+        self.root_state = state
+        self.heuristic_fn = heuristic_fn
+        self.weight = weight
+        self.max_nodes = max_nodes
+        self.engine: Optional[BWASGpu] = None
+        self.popped_ids: List[int] = []
+
+    def ensure(self, batch_size: int) -> BWASGpu:
+        if self.engine is None or self.engine.B != batch_size:
+            assert self.engine is None, "batch_size must not change during a search"
+            self.engine = BWASGpu(_env_name(self.env), _device_heuristic(self.heuristic_fn, self.env), self.weight, batch_size,
+                                  max_nodes=self.max_nodes, semantics="python")
+            self.engine.reset(self.env.pack([self.root_state])[0])
+        return self.engine
+
+    # ---- Node materialisation -----------------------------------------------------------------------
+    def node_chain(self, node_id: int) -> Node:
+        eng = self.engine
+        ids = [node_id]
+        A = eng.A
+        sp = eng.slot_parent
+        while ids[-1] != 0:
+            ids.append(int(sp[ids[-1] // A].item()) & 0xFFFFFFFF)
+        ids.reverse()
+        states = self.env.unpack(eng.node_states(ids))
+        g = eng.node_g[torch.tensor(ids, device=eng.dev)].cpu().numpy()
+        sv = eng.node_solved[torch.tensor(ids, device=eng.dev)].cpu().numpy()
+        parent: Optional[Node] = None
+        for k, nid in enumerate(ids):
+            parent = Node(states[k], float(g[k]), bool(sv[k]), None if nid == 0 else nid % A, parent)
+        return parent
+
+
+class AStar:
+    def __init__(self, states: List[State], env: Environment, heuristic_fn: Callable, weights: List[float],
+                 max_nodes: Optional[int] = None):
+        self.env: Environment = env
+        self.weights: List[float] = weights
+        self.step_num: int = 0
+        self.timings: Dict[str, float] = {"pop": 0.0, "expand": 0.0, "check": 0.0, "heur": 0.0, "add": 0.0, "itr": 0.0}
+        mn = int(max_nodes or os.environ.get("DCB_MAX_NODES", 1 << 24))
+        self.instances: List[Instance] = [Instance(env, s, heuristic_fn, w, mn) for s, w in zip(states, weights)]
+        self._batch_size: Optional[int] = None
+
+    def _engines(self, batch_size: int) -> List[BWASGpu]:
+        return [inst.ensure(batch_size) for inst in self.instances]
+
+    def step(self, heuristic_fn: Callable, batch_size: int, include_solved: bool = False, verbose: bool = False):
+        t_itr = time.time()
+        engines = self._engines(batch_size)
+        for inst, eng in zip(self.instances, engines):
+            if not include_solved and eng.goal_ids:
+                continue
+            before = dict(eng.timings)
+            eng.step()
+            inst.popped_ids.extend(eng.popped_ids[:eng.last_popped].cpu().numpy().view(np.uint32).tolist())
+            for k in ("pop", "expand", "check", "heur", "add"):
+                self.timings[k] += eng.timings[k] - before[k]
+        itr = time.time() - t_itr
+        self.timings["itr"] += itr
+        if verbose:
+            print("Itr: %i, Times - pop: %.2f, expand: %.2f, check: %.2f, heur: %.2f, add: %.2f, itr: %.2f\n" % (
+                self.step_num, self.timings["pop"], self.timings["expand"], self.timings["check"], self.timings["heur"],
+                self.timings["add"], itr))
+        self.step_num += 1
+
+    def has_found_goal(self) -> List[bool]:
+        return [inst.engine is not None and len(inst.engine.goal_ids) > 0 for inst in self.instances]
+
+    def get_goal_nodes(self, inst_idx) -> List[Node]:
+        inst = self.instances[inst_idx]
+        return [inst.node_chain(g) for g in (inst.engine.goal_ids if inst.engine else [])]
+
+    def get_goal_node_smallest_path_cost(self, inst_idx) -> Node:
+        inst = self.instances[inst_idx]
+        return inst.node_chain(inst.engine.goal_id)
+
+    def get_num_nodes_generated(self, inst_idx: int) -> int:
+        eng = self.instances[inst_idx].engine
+        return eng.nodes_generated if eng else 0
+
+    def get_popped_nodes(self) -> List[List[Node]]:
+        return [[inst.node_chain(i) for i in inst.popped_ids] for inst in self.instances]
+
+
+# =====================================================================================================
+# CLI
+# =====================================================================================================
+def main(argv: Optional[List[str]] = None):
+    parser = ArgumentParser()
+    parser.add_argument("--states", type=str, required=True, help="File containing states to solve")
+    parser.add_argument("--model_dir", type=str, required=True, help="Directory of nnet model")
+    parser.add_argument("--env", type=str, required=True, help="Environment: cube3, puzzle15, puzzle24, puzzle35, puzzle48")
+    parser.add_argument("--batch_size", type=int, default=1, help="Batch size for BWAS")
+    parser.add_argument("--weight", type=float, default=1.0, help="Weight of path cost")
+    parser.add_argument("--language", type=str, default="cuda", help="cuda (=cpp semantics on the GPU), cpp, or python")
+    parser.add_argument("--results_dir", type=str, required=True, help="Directory to save results")
+    parser.add_argument("--start_idx", type=int, default=0, help="")
+    parser.add_argument("--nnet_batch_size", type=int, default=None,
+                        help="States evaluated by the neural network at a time; does not affect results")
+    parser.add_argument("--verbose", action="store_true", default=False, help="Set for verbose")
+    parser.add_argument("--debug", action="store_true", default=False, help="Set when debugging")
+    parser.add_argument("--nnet_precision", type=str, default=None, help="fp32 (default, parity) | tf32 | bf16")
+    parser.add_argument("--max_nodes", type=int, default=1 << 26, help="Node arena capacity per search")
+    parser.add_argument("--num_states", type=int, default=None, help="Solve only the first N states (after --start_idx)")
+    args = parser.parse_args(argv)
+
+    if not os.path.exists(args.results_dir):
+        os.makedirs(args.results_dir)
+    results_file = "%s/results.pkl" % args.results_dir
+    output_file = "%s/output.txt" % args.results_dir
+    stdout_prev = sys.stdout
+    if not args.debug:
+        sys.stdout = data_utils.Logger(output_file, "w")
+    try:
+        input_data = pickle.load(open(args.states, "rb"))
+        states: List[State] = input_data["states"][args.start_idx:]
+        if args.num_states is not None:
+            states = states[:args.num_states]
+        env: Environment = env_utils.get_environment(args.env)
+        results: Dict[str, Any] = {"states": states}
+        lang = args.language.lower()
+        if lang == "python":
+            solns, paths, times, num_nodes_gen = bwas_python(args, env, states)
+        elif lang in ("cuda", "cpp"):
+            solns, paths, times, num_nodes_gen = bwas_cuda(args, env, states)
+        else:
+            raise ValueError("Unknown language %s" % args.language)
+        results["solutions"] = solns
+        results["paths"] = paths
+        results["times"] = times
+        results["num_nodes_generated"] = num_nodes_gen
+        pickle.dump(results, open(results_file, "wb"), protocol=-1)
+    finally:
+        sys.stdout = stdout_prev
+
+
+def _load_heuristic(args, env: Environment):
+    device, devices, on_gpu = nnet_utils.get_device()
+    print("device: %s, devices: %s, on_gpu: %s" % (device, devices, on_gpu))
+    if not on_gpu:
+        raise RuntimeError("the BWAS engine is CUDA-only; no GPU is visible and there is no CPU fallback")
+    return nnet_utils.load_heuristic_fn(args.model_dir, device, on_gpu, env.get_nnet_model(), env, clip_zero=True,
+                                        batch_size=args.nnet_batch_size, precision=args.nnet_precision)
+
+
+def bwas_python(args, env: Environment, states: List[State]):
+    """astar.py:400-454 on the GPU engine (Python semantics)."""
+    heuristic_fn = _load_heuristic(args, env)
+    solns, paths, times, num_nodes_gen = [], [], [], []
+    for state_idx, state in enumerate(states):
+        start_time = time.time()
+        num_itrs = 0
+        astar = AStar([state], env, heuristic_fn, [args.weight], max_nodes=args.max_nodes)
+        while not min(astar.has_found_goal()):
+            astar.step(heuristic_fn, args.batch_size, verbose=args.verbose)
+            num_itrs += 1
+        goal_node = astar.get_goal_node_smallest_path_cost(0)
+        path, soln, path_cost = get_path(goal_node)
+        n_gen = astar.get_num_nodes_generated(0)
+        solve_time = time.time() - start_time
+        solns.append(soln); paths.append(path); times.append(solve_time); num_nodes_gen.append(n_gen)
+        assert search_utils.is_valid_soln(state, soln, env)
+        timing_str = ", ".join(["%s: %.2f" % (k, v) for k, v in astar.timings.items()])
+        print("Times - %s, num_itrs: %i" % (timing_str, num_itrs))
+        print("State: %i, SolnCost: %.2f, # Moves: %i, # Nodes Gen: %s, Time: %.2f" % (
+            state_idx, path_cost, len(soln), format(n_gen, ","), solve_time))
+        astar.instances[0].engine = None        # release HBM before the next state
+    return solns, paths, times, num_nodes_gen
+
+
+def bwas_cuda(args, env: Environment, states: List[State]):
+    """The `--language cpp` flow of astar.py:457-568 with the child process, socket and stdout protocol
+    replaced by in-process calls into the C ABI: one engine, states solved one after the other."""
+    heuristic_fn = _load_heuristic(args, env)
+    engine = BWASGpu(args.env, heuristic_fn.device_fn, args.weight, args.batch_size, max_nodes=args.max_nodes, semantics="cpp")
+    packed = env.pack(states)
+    solns, paths, times, num_nodes_gen = [], [], [], []
+    for state_idx, state in enumerate(states):
+        res = engine.solve(packed[state_idx])
+        if res.moves is None:
+            raise RuntimeError("OPEN exhausted without reaching the goal for state %d" % state_idx)
+        soln = [int(m) for m in res.moves]
+        path: List[State] = [state]
+        cur = state
+        tcs: List[float] = []
+        for move in soln:                                   # astar.py:539-546
+            nxt, tc = env.next_state([cur], move)
+            cur = nxt[0]
+            path.append(cur); tcs.append(tc[0])
+        solns.append(soln); paths.append(path); times.append(res.solve_time); num_nodes_gen.append(res.nodes_generated)
+        assert search_utils.is_valid_soln(state, soln, env)
+        if args.verbose:
+            print("Times - %s, num_itrs: %i" % (", ".join("%s: %.2f" % kv for kv in res.timings.items()), res.iterations))
+        print("State: %i, SolnCost: %.2f, # Moves: %i, # Nodes Gen: %s, Time: %.2f" % (
+            state_idx, sum(tcs), len(soln), format(res.nodes_generated, ","), res.solve_time))
+    return solns, paths, times, num_nodes_gen
+
+
+if __name__ == "__main__":
+    main()

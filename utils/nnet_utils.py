@@ -1,0 +1,2 @@
+"""Alias of deepcubea_b200.utils.nnet_utils (reference import path)."""
+from deepcubea_b200.utils.nnet_utils import *  # noqa: F401,F403
