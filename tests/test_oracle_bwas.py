@@ -1,0 +1,65 @@
+"""CPU tier: the oracle's BWAS restatement vs the REAL reference binary (oracle/_ref, compiled from the
+reference's cpp/*.cpp) over the reference's socket protocol, with a tie-free heuristic so that the C++ heap's
+unspecified tie order cannot matter: moves, nodes generated and iteration count must be identical."""
+import random
+
+import numpy as np
+import pytest
+
+from oracle import oracle_env as O
+from oracle.oracle_bwas import bwas, misplaced_heuristic
+from oracle.ref_runner import HeuristicServer, have_reference_binary, run_reference_bwas
+
+
+def _tie_free(env):
+    base = misplaced_heuristic(env)
+    wj = (np.arange(env.state_dim) + 1).astype(np.int64)
+
+    def h(states):
+        pert = ((states.astype(np.int64) * wj[None]).sum(axis=1) % 1009).astype(np.float32) / np.float32(65536.0)
+        return (base(states) + pert).astype(np.float32)
+    return h
+
+
+@pytest.mark.skipif(not have_reference_binary(), reason="oracle/_ref/parallel_weighted_astar not built (needs /root/reference)")
+@pytest.mark.parametrize("name,back,batch,weight", [("cube3", (4, 8), 100, 0.8), ("cube3", (5, 9), 10, 0.6), ("cube3", (3, 6), 1, 1.0),
+                                                     ("puzzle15", (10, 24), 20, 0.8), ("puzzle48", (8, 16), 50, 0.6)])
+def test_oracle_bwas_equals_reference_binary(name, back, batch, weight):
+    env = O.get_oracle_env(name)
+    h = _tie_free(env)
+    np.random.seed(21); random.seed(21)
+    states, _ = env.generate_states(4, back)
+    srv = HeuristicServer(env.state_dim, h)
+    try:
+        for s in states:
+            ref = run_reference_bwas(name, s, weight, batch, srv, timeout=120)
+            ours = bwas(env, s, h, weight, batch, batch_dedup="sequential")
+            assert ours["moves"] == ref["moves"]
+            assert ours["nodes_generated"] == ref["nodes_generated"]
+            assert ours["iterations"] == ref["iterations"]
+            cur = s[None]
+            for mv in ref["moves"]:
+                cur = env.move(cur, mv)
+            assert env.is_solved(cur)[0]
+    finally:
+        srv.close()
+
+
+@pytest.mark.parametrize("name", ["cube3", "puzzle15"])
+def test_min_and_sequential_dedup_agree_on_validity(name):
+    """The GPU's in-batch duplicate rule ("min") vs the reference's child-order rule: both return valid
+    solutions; lengths agree on these cases (the rule only removes dominated duplicates)."""
+    env = O.get_oracle_env(name)
+    h = misplaced_heuristic(env)
+    np.random.seed(5); random.seed(5)
+    states, _ = env.generate_states(5, (4, 9) if name == "cube3" else (10, 30))
+    for s in states:
+        a = bwas(env, s, h, 0.8, 50, batch_dedup="min")
+        b = bwas(env, s, h, 0.8, 50, batch_dedup="sequential")
+        for r in (a, b):
+            cur = s[None]
+            for mv in r["moves"]:
+                cur = env.move(cur, mv)
+            assert env.is_solved(cur)[0]
+        assert len(a["moves"]) == len(b["moves"])
+        assert a["nodes_generated"] <= b["nodes_generated"]
