@@ -164,11 +164,16 @@ def run_ours(args):
     launches0 = eng.kernel_launches
     sampler = ClockSampler(local); sampler.start()
     barrier()
+    prof = os.environ.get("DCB_CUDA_PROFILER") == "1"     # `ncu --profile-from-start off`: capture the timed region only
+    if prof:
+        torch.cuda.profiler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     nodes, solved, lens = run_steps(args.steps, cursor)
     ev1.record()
     barrier()
+    if prof:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
