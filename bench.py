@@ -112,6 +112,9 @@ def build_heuristic(device, precision: str):
                 m.running_mean.normal_(0, 0.1); m.running_var.uniform_(0.5, 1.5)
         src = "random-init weights (seed 0)"
     model.eval()
+    if precision in ("fp16x3", "fp16"):                 # hand-written tcgen05 dense layers (csrc/resnet_kernels.cu)
+        from deepcubea_b200.nnet.tc_resnet import TcResnet
+        return TcResnet(model, device, mode=precision), src
     return DeviceHeuristic(FoldedResnet(model, mode=precision).to(device), chunk=1 << 17), src
 
 
@@ -238,7 +241,10 @@ def run_ours(args):
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
         line = {"metric": METRIC, "value": nodes / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "u8 states / u64 hashes / f32 costs; heuristic GEMMs %s" % args.nnet_precision,
+                "dtype": "u8 states / u64 hashes / f32 costs; heuristic GEMMs %s" % {
+                    "fp32": "fp32 (cuBLAS SGEMM)", "tf32": "tf32 (cuBLAS)", "bf16": "bf16 (cuBLAS)",
+                    "fp16x3": "fp16 hi/lo x3 products, fp32 accumulate (tcgen05, fp32-parity mode)",
+                    "fp16": "fp16, fp32 accumulate (tcgen05)"}[args.nnet_precision],
                 "data": "synthetic cube3 scrambles (generate_states(n,(0,26)), seed 1234); " + weights_src,
                 "config": {"workload": "cube3 A* weight=0.8 batch_size=20000, scrambles depth<=26 (BASELINE configs[1])",
                            "step": "one BWAS iteration (pop<=20000, expand 12x, CLOSED, heuristic on survivors, push)",
@@ -348,7 +354,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16"])
+    ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"])
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -1,0 +1,141 @@
+"""Cost-to-go ResNet on the hand-written tcgen05 GEMM (csrc/resnet_kernels.cu).
+
+Host side of `dcb_resnet_gemm`: folds eval-mode BatchNorm into the Linear layers (float64 -> float32, as
+nnet/folded.py), pads every layer to the kernel's tile grid (N to 256, K to 64), pre-scales each weight matrix by
+a power of two so its fp16 hi/lo split stays in fp16's normal range, and splits it as W = hi + lo.
+Activations flow between layers as fp16 hi (+ lo) arrays written by the GEMM epilogue; only the final
+fc_out dot product (pytorch_models.py:85) leaves the tensor cores.
+
+modes:  "fp16x3"  A_hi*W_hi + A_hi*W_lo + A_lo*W_hi, fp32 accumulate  -> fp32-level accuracy (parity mode)
+        "fp16"    A_hi*W_hi only                                      -> 3x fewer MMAs, ~1e-2 accuracy
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+from torch import nn
+
+from .. import _lib
+from .._lib import check, ptr
+from .folded import _fold
+
+
+def _pad_to(v: int, m: int) -> int:
+    return -(-v // m) * m
+
+
+class _Layer:
+    def __init__(self, w: torch.Tensor, b: torch.Tensor, device, split: bool, k_align: int):
+        n, k = w.shape
+        self.n, self.k = n, k
+        # K must equal the padded width of the activation matrix that feeds this layer (the previous layer's N)
+        self.np_, self.kp = _pad_to(n, 256), _pad_to(k, k_align)
+        # power-of-two pre-scale: largest |w| lands in [2^9, 2^10) -> hi and lo both normal fp16 numbers
+        amax = float(w.abs().max())
+        e = 0 if amax == 0 else int(torch.floor(torch.log2(torch.tensor(amax))).item())
+        self.wexp = 9 - e
+        ws = torch.zeros((self.np_, self.kp), dtype=torch.float32)
+        ws[:n, :k] = w * (2.0 ** self.wexp)
+        hi = ws.to(torch.float16)
+        lo = (ws - hi.float()).to(torch.float16)
+        self.w_hi = hi.to(device).contiguous()
+        self.w_lo = lo.to(device).contiguous() if split else None
+        bias = torch.zeros(self.np_, dtype=torch.float32)
+        bias[:n] = b
+        self.bias = bias.to(device)
+        self.scale = 2.0 ** (-self.wexp)
+
+
+class TcResnet:
+    """Callable: nnet-input u8 [m, S] on the device -> cost-to-go f32 [m] on the device."""
+
+    def __init__(self, model: nn.Module, device: torch.device, mode: str = "fp16x3", chunk: int = 1 << 16):
+        assert mode in ("fp16x3", "fp16")
+        self.lib = _lib.load()
+        self.mode, self.dev, self.chunk = mode, device, chunk
+        self.split = mode == "fp16x3"
+        self.state_dim, self.depth = model.state_dim, model.one_hot_depth
+        assert self.depth > 0, "the tcgen05 path encodes a one-hot input"
+        bn = model.batch_norm
+        folded = [_fold(model.fc1, model.bn1 if bn else None), _fold(model.fc2, model.bn2 if bn else None)]
+        for blk in model.blocks:
+            folded += ([_fold(blk[0], blk[1]), _fold(blk[2], blk[3])] if bn else [_fold(blk[0], None), _fold(blk[1], None)])
+        self.layers: List[_Layer] = [_Layer(w, b, device, self.split, 64 if i == 0 else 256) for i, (w, b) in enumerate(folded)]
+        for prev, cur in zip(self.layers[:-1], self.layers[1:]):
+            assert cur.kp == prev.np_, "activation width mismatch between consecutive layers"
+        self.num_blocks = len(model.blocks)
+        w_out, b_out = _fold(model.fc_out, None)
+        assert w_out.shape[0] == 1
+        self.w_out = w_out[0].contiguous().to(device)
+        self.b_out = float(b_out[0])
+        self.k0 = self.layers[0].kp
+        assert self.layers[0].k == self.state_dim * self.depth
+        self._bufs = {}
+        self.flops_per_row = sum(2 * l.np_ * l.kp for l in self.layers)
+
+    def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        key = (name, cols)
+        t = self._bufs.get(key)
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1), cols), dtype=torch.float16, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    K_CHUNK = 1024      # longest K accumulated in one TMEM accumulator in parity mode (see resnet_kernels.cu)
+
+    def _gemm(self, layer: _Layer, a_hi, a_lo, skip_hi, skip_lo, relu: bool, out_hi, out_lo, m: int, st: int) -> None:
+        lib = self.lib
+        use_lo = a_lo is not None and layer.w_lo is not None
+        lda, ldw = a_hi.shape[1], layer.kp
+        chunk = self.K_CHUNK if self.split else layer.kp
+        n_chunks = -(-layer.kp // chunk)
+        part = self._buf32("partial", m, layer.np_) if n_chunks > 1 else None
+        for c in range(n_chunks):
+            k0 = c * chunk
+            kc = min(chunk, layer.kp - k0)
+            last = c == n_chunks - 1
+            check(lib.dcb_resnet_gemm(a_hi.data_ptr() + 2 * k0, (a_lo.data_ptr() + 2 * k0) if use_lo else None, lda,
+                                      layer.w_hi.data_ptr() + 2 * k0, (layer.w_lo.data_ptr() + 2 * k0) if layer.w_lo is not None else None, ldw,
+                                      ptr(layer.bias), layer.scale, ptr(skip_hi) if last else None, ptr(skip_lo) if last else None,
+                                      1 if relu else 0, ptr(out_hi), ptr(out_lo), None,
+                                      ptr(part) if c > 0 else None, None if last else ptr(part), m, layer.np_, kc, st), "dcb_resnet_gemm")
+
+    def _buf32(self, name: str, rows: int, cols: int) -> torch.Tensor:
+        key = (name, cols, 32)
+        t = self._bufs.get(key)
+        if t is None or t.shape[0] < rows:
+            t = torch.empty((max(rows, 1), cols), dtype=torch.float32, device=self.dev)
+            self._bufs[key] = t
+        return t
+
+    @torch.no_grad()
+    def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.shape[1] == self.state_dim
+        n = x.shape[0]
+        out = torch.empty(n, dtype=torch.float32, device=self.dev)
+        st = torch.cuda.current_stream(self.dev).cuda_stream
+        sp = self.split
+        for i0 in range(0, n, self.chunk):
+            m = min(self.chunk, n - i0)
+            xin = x[i0:i0 + m]
+            a0 = self._buf("onehot", m, self.k0)
+            check(self.lib.dcb_onehot_fp16(ptr(xin), m, self.state_dim, self.depth, self.k0, ptr(a0), st), "dcb_onehot_fp16")
+            l0, l1 = self.layers[0], self.layers[1]
+            h1_hi = self._buf("h1_hi", m, l0.np_)
+            h1_lo = self._buf("h1_lo", m, l0.np_) if sp else None
+            self._gemm(l0, a0, None, None, None, True, h1_hi, h1_lo, m, st)            # one-hot input is exact: hi only
+            width = l1.np_
+            x_hi, x_lo = self._buf("x_hi", m, width), (self._buf("x_lo", m, width) if sp else None)
+            self._gemm(l1, h1_hi, h1_lo, None, None, True, x_hi, x_lo, m, st)
+            t_hi, t_lo = self._buf("t_hi", m, width), (self._buf("t_lo", m, width) if sp else None)
+            y_hi, y_lo = self._buf("y_hi", m, width), (self._buf("y_lo", m, width) if sp else None)
+            for k in range(self.num_blocks):
+                la, lb = self.layers[2 + 2 * k], self.layers[3 + 2 * k]
+                self._gemm(la, x_hi, x_lo, None, None, True, t_hi, t_lo, m, st)
+                self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, y_hi, y_lo, m, st)        # relu(fc(t) + skip)
+                x_hi, y_hi = y_hi, x_hi
+                x_lo, y_lo = y_lo, x_lo
+            check(self.lib.dcb_rowdot(ptr(x_hi), ptr(x_lo), ptr(self.w_out), self.b_out, m, self.w_out.numel(), width,
+                                      out.data_ptr() + 4 * i0, st), "dcb_rowdot")
+        return out

@@ -185,7 +185,7 @@ def main(argv: Optional[List[str]] = None):
                         help="States evaluated by the neural network at a time; does not affect results")
     parser.add_argument("--verbose", action="store_true", default=False, help="Set for verbose")
     parser.add_argument("--debug", action="store_true", default=False, help="Set when debugging")
-    parser.add_argument("--nnet_precision", type=str, default=None, help="fp32 (default, parity) | tf32 | bf16")
+    parser.add_argument("--nnet_precision", type=str, default=None, help="fp32 (default) | tf32 | bf16 (cuBLAS) | fp16x3 | fp16 (hand-written tcgen05)")
     parser.add_argument("--max_nodes", type=int, default=1 << 26, help="Node arena capacity per search")
     parser.add_argument("--num_states", type=int, default=None, help="Solve only the first N states (after --start_idx)")
     args = parser.parse_args(argv)

@@ -86,14 +86,20 @@ def load_heuristic_fn(nnet_dir: str, device: torch.device, on_gpu: bool, nnet: n
                       clip_zero: bool = False, gpu_num: int = -1, batch_size: Optional[int] = None,
                       precision: Optional[str] = None):
     """nnet_utils.py:206-221.  `precision` (or $DCB_NNET_PRECISION) selects the inference arithmetic of the
-    folded network: fp32 (parity, default) | tf32 | bf16."""
+    network: fp32 (cuBLAS, default) | tf32 | bf16 | fp16x3 (tcgen05, fp32-parity) | fp16 (tcgen05)."""
     if gpu_num >= 0 and on_gpu:
         os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu_num)
     nnet = load_nnet("%s/model_state_dict.pt" % nnet_dir, nnet, device=device)
     nnet.eval()
     nnet.to(device)
     if on_gpu:
-        from ..nnet.folded import FoldedResnet
         mode = precision or os.environ.get("DCB_NNET_PRECISION", "fp32")
+        if mode in ("fp16x3", "fp16"):            # hand-written tcgen05 dense layers
+            from ..nnet.tc_resnet import TcResnet
+            tc = TcResnet(nnet, device, mode=mode, chunk=batch_size or (1 << 16))
+            fn = get_heuristic_fn(nnet, device, env, clip_zero=clip_zero, batch_size=batch_size)
+            fn.device_fn = tc
+            return fn
+        from ..nnet.folded import FoldedResnet
         nnet = FoldedResnet(nnet, mode=mode).to(device)
     return get_heuristic_fn(nnet, device, env, clip_zero=clip_zero, batch_size=batch_size)

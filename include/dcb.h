@@ -187,6 +187,30 @@ int dcb_compute_cost(const float *d_h, const uint32_t *d_ids, const uint32_t *d_
 int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_id, int32_t max_len,
                          uint8_t *d_moves, int32_t *d_len, void *stream);
 
+/* ---- cost-to-go network (utils/pytorch_models.py:45-86), dense layers on tcgen05 tensor cores ------
+ * Eval-mode BatchNorm is folded into the preceding Linear by the caller (deepcubea_b200/nnet/tc_resnet.py).
+ * Activations and weights are fp16 "hi" arrays plus optional fp16 "lo" arrays with x = hi + lo (22 significand
+ * bits).  One call = one layer (or one K chunk of it):
+ *     OUT[m][n] = act( scale * ( PARTIAL_IN[m][n] + sum_k A[m][k] * W[n][k] ) + bias[n] + SKIP[m][n] )
+ * with the products A_hi*W_lo (if d_w_lo), A_lo*W_hi (if d_a_lo and d_w_lo) and A_hi*W_hi swept over K in that
+ * order into one fp32 TMEM accumulator (small terms first: the tensor core's accumulation truncates).
+ * Row-major, K-major operands: A [m][k_padded] with leading dimension lda, W [n_padded][k_padded] with leading
+ * dimension ldw (elements, multiples of 8), SKIP / OUT / PARTIAL [m][n_padded]; n_padded % 256 == 0,
+ * k_padded % 64 == 0; padding rows / cols of W and bias must be zero.
+ * If d_partial_out is set the call only writes the raw fp32 sum (PARTIAL_IN + A*W) there -- used to split a long K
+ * into chunks of <= 1024 chained through fp32.  Otherwise OUT is written as fp16 hi (+ lo if d_out_lo) (+ fp32 if
+ * d_out_f32); relu != 0 applies max(.,0). */
+int dcb_resnet_gemm(const void *d_a_hi, const void *d_a_lo, int64_t lda, const void *d_w_hi, const void *d_w_lo, int64_t ldw,
+                    const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
+                    void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, int64_t m,
+                    int32_t n_padded, int32_t k_padded, void *stream);
+/* F.one_hot of the nnet input (pytorch_models.py:49-52) as fp16 [m][k_padded], column = position*depth + value. */
+int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int32_t depth, int32_t k_padded, void *d_out,
+                    void *stream);
+/* fc_out (pytorch_models.py:85): d_out[m] = sum_{n<n_valid} (x_hi+x_lo)[m][n] * d_w[n] + bias, fp32. */
+int dcb_rowdot(const void *d_x_hi, const void *d_x_lo, const float *d_w, float bias, int64_t m, int32_t n_valid, int32_t ld,
+               float *d_out, void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

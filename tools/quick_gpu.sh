@@ -1,8 +1,5 @@
-set -x
 cd $GRAFT_REPO_ROOT
-DCB_CUDA_PROFILER=1 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r01.csv python bench.py --steps 3 --warmup 4 --no_cpu_baseline > gpurun_out/bench_under_ncu.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:expand_kernel -c 8 -f -o gpurun_out/prof_expand_r01 python tools/prof_expand.py > gpurun_out/prof_expand.log 2>&1
-tail -3 gpurun_out/prof_expand.log
-DCB_CUDA_PROFILER=1 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:'closed_|open_|child_meta|compact|gather_nnet|cost_kernel' -c 60 -f -o gpurun_out/prof_bwas_r01 python bench.py --steps 2 --warmup 6 --no_cpu_baseline > gpurun_out/prof_bwas.log 2>&1
-tail -3 gpurun_out/prof_bwas.log
-ls -la gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -s -x 2>&1 | grep -E "max \|err\||assert|passed|failed|Error" | head -12
+python tools/bench_nnet.py 2>&1 | tail -5
+for p in fp16x3 fp16; do python bench.py --steps 30 --warmup 8 --no_cpu_baseline --nnet_precision $p 2>gpurun_out/bench_$p.err | tee gpurun_out/bench_$p.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read()); print(d['dtype'][-40:], 'value %.3g'%d['value'], 'ms/step %.2f'%d['ms_per_step'], 'e2e %.3g'%d['e2e']['value'], 'solved', d['config']['solved_in_timed_region'], 'len', d['config']['mean_solution_len'])"; tail -2 gpurun_out/bench_$p.err; done
