@@ -124,8 +124,8 @@ def run_ours(args):
     import torch.distributed as dist
     from deepcubea_b200 import _lib, ops
     from deepcubea_b200.search.bwas_gpu import BWASGpu
-    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
+    from deepcubea_b200.search import sharding
+    rank, world, local = sharding.world()
     if not torch.cuda.is_available():
         raise _lib.DcbError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
@@ -138,12 +138,12 @@ def run_ours(args):
     eng = BWASGpu("cube3", heur, WEIGHT, BATCH, max_nodes=max_nodes, device=dev)
     # instances shard by rank (instance i -> rank i % world): weak scaling, no data-path collective
     n_inst = max(4, steps_total // 8)
-    states = make_states(n_inst * world, seed=1234)[rank::world]
+    all_states = make_states(n_inst * world, seed=1234)
+    states = all_states[sharding.shard_indices(len(all_states), rank, world)]
 
     def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        sharding.completion_barrier()
 
     def run_steps(k, cursor):
         """k BWAS iterations over consecutive start states; returns (nodes, solved, lens, cursor)."""
@@ -222,16 +222,13 @@ def run_ours(args):
                                "note": "A* launches move ~16 MB each: launch-latency bound, not HBM bound"}
         del par, ch
     # ---- reduce over ranks -------------------------------------------------------------------------------------
+    len_sum = sum(lens)
     if world > 1:
-        t_ms = torch.tensor([ms, e_sec * 1e3], dtype=torch.float64, device=dev)
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        cnt = torch.tensor([nodes, e_nodes, launches, solved, sum(lens), h2d, d2h], dtype=torch.float64, device=dev)
+        nodes, ms = sharding.reduce_throughput(nodes, ms, dev)            # nodes SUM over ranks, device time MAX over ranks
+        e_nodes, e_sec = sharding.reduce_throughput(e_nodes, e_sec, dev)
+        cnt = torch.tensor([launches, solved, len_sum, h2d, d2h], dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        ms, e_ms = t_ms.tolist()
-        nodes, e_nodes, launches, solved, len_sum, h2d, d2h = cnt.tolist()
-        e_sec = e_ms * 1e-3
-    else:
-        len_sum = sum(lens)
+        launches, solved, len_sum, h2d, d2h = cnt.tolist()
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -354,7 +351,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp32"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"])
+    ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp16x3"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"],
+                    help="heuristic arithmetic: fp16x3 = hand-written tcgen05, fp32-parity (max err 2e-5 vs fp64; default); fp32 = cuBLAS SGEMM")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:

@@ -215,7 +215,8 @@ def main(argv: Optional[List[str]] = None):
         results["paths"] = paths
         results["times"] = times
         results["num_nodes_generated"] = num_nodes_gen
-        pickle.dump(results, open(results_file, "wb"), protocol=-1)
+        if int(os.environ.get("RANK", 0)) == 0:
+            pickle.dump(results, open(results_file, "wb"), protocol=-1)
     finally:
         sys.stdout = stdout_prev
 
@@ -256,30 +257,66 @@ def bwas_python(args, env: Environment, states: List[State]):
 
 def bwas_cuda(args, env: Environment, states: List[State]):
     """The `--language cpp` flow of astar.py:457-568 with the child process, socket and stdout protocol
-    replaced by in-process calls into the C ABI: one engine, states solved one after the other."""
+    replaced by in-process calls into the C ABI: one engine per GPU, states solved one after the other.
+    Under torchrun (one process per GPU) the start states are sharded round-robin over the ranks and rank 0
+    merges the results; nothing else crosses GPUs."""
+    import torch.distributed as dist
+
+    from ..search import sharding
+    rank, world_size, local = sharding.world()
+    if world_size > 1:
+        torch.cuda.set_device(local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     heuristic_fn = _load_heuristic(args, env)
     engine = BWASGpu(args.env, heuristic_fn.device_fn, args.weight, args.batch_size, max_nodes=args.max_nodes, semantics="cpp")
     packed = env.pack(states)
+    my_idx = sharding.shard_indices(len(states), rank, world_size)
+    if world_size > 1:
+        local_res = []
+        for state_idx in my_idx:
+            res = engine.solve(packed[state_idx])
+            if res.moves is None:
+                raise RuntimeError("OPEN exhausted without reaching the goal for state %d" % state_idx)
+            local_res.append((state_idx, ([int(m) for m in res.moves], res.solve_time, res.nodes_generated)))
+        sharding.completion_barrier()
+        merged = sharding.gather_results(local_res, len(states))
+        if rank != 0:
+            return [], [], [], []
+        solved = {i: r for i, r in enumerate(merged)}
+    else:
+        solved = None
     solns, paths, times, num_nodes_gen = [], [], [], []
     for state_idx, state in enumerate(states):
+        if solved is not None:
+            from types import SimpleNamespace
+            mv, tm, ng = solved[state_idx]
+            res = SimpleNamespace(moves=mv, solve_time=tm, nodes_generated=ng, timings={}, iterations=0)
+            _finish_state(args, env, state_idx, state, res, solns, paths, times, num_nodes_gen)
+            continue
         res = engine.solve(packed[state_idx])
         if res.moves is None:
             raise RuntimeError("OPEN exhausted without reaching the goal for state %d" % state_idx)
-        soln = [int(m) for m in res.moves]
-        path: List[State] = [state]
-        cur = state
-        tcs: List[float] = []
-        for move in soln:                                   # astar.py:539-546
-            nxt, tc = env.next_state([cur], move)
-            cur = nxt[0]
-            path.append(cur); tcs.append(tc[0])
-        solns.append(soln); paths.append(path); times.append(res.solve_time); num_nodes_gen.append(res.nodes_generated)
-        assert search_utils.is_valid_soln(state, soln, env)
-        if args.verbose:
-            print("Times - %s, num_itrs: %i" % (", ".join("%s: %.2f" % kv for kv in res.timings.items()), res.iterations))
-        print("State: %i, SolnCost: %.2f, # Moves: %i, # Nodes Gen: %s, Time: %.2f" % (
-            state_idx, sum(tcs), len(soln), format(res.nodes_generated, ","), res.solve_time))
+        _finish_state(args, env, state_idx, state, res, solns, paths, times, num_nodes_gen)
     return solns, paths, times, num_nodes_gen
+
+
+def _finish_state(args, env, state_idx, state, res, solns, paths, times, num_nodes_gen):
+    """Replay the moves into a path, validate, record and print (astar.py:539-562)."""
+    soln = [int(m) for m in res.moves]
+    path: List[State] = [state]
+    cur = state
+    tcs: List[float] = []
+    for move in soln:
+        nxt, tc = env.next_state([cur], move)
+        cur = nxt[0]
+        path.append(cur); tcs.append(tc[0])
+    solns.append(soln); paths.append(path); times.append(res.solve_time); num_nodes_gen.append(res.nodes_generated)
+    assert search_utils.is_valid_soln(state, soln, env)
+    if args.verbose and res.timings:
+        print("Times - %s, num_itrs: %i" % (", ".join("%s: %.2f" % kv for kv in res.timings.items()), res.iterations))
+    print("State: %i, SolnCost: %.2f, # Moves: %i, # Nodes Gen: %s, Time: %.2f" % (
+        state_idx, sum(tcs), len(soln), format(res.nodes_generated, ","), res.solve_time))
 
 
 if __name__ == "__main__":
