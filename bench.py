@@ -165,6 +165,7 @@ def run_ours(args):
     # ---- device-resident timed region ----------------------------------------------------------------
     eng.expand_events = []
     launches0 = eng.kernel_launches
+    kept0 = eng.total_kept
     sampler = ClockSampler(local); sampler.start()
     barrier()
     prof = os.environ.get("DCB_CUDA_PROFILER") == "1"     # `ncu --profile-from-start off`: capture the timed region only
@@ -180,6 +181,7 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
+    kept = eng.total_kept - kept0
     in_loop = [(a.elapsed_time(b), n) for a, b, n in eng.expand_events]
     eng.expand_events = None
     # ---- end-to-end through the public API: host start state in, host solution out ---------------------
@@ -247,7 +249,8 @@ def run_ours(args):
                            "step": "one BWAS iteration (pop<=20000, expand 12x, CLOSED, heuristic on survivors, push)",
                            "instances_per_gpu": len(states), "max_nodes": max_nodes, "parallelism": "instances sharded over %d GPU(s)" % world,
                            "l2": "working set (arena+CLOSED+OPEN) >> L2; roofline launches write 1.7 GB each",
-                           "solved_in_timed_region": int(solved), "mean_solution_len": (len_sum / solved) if solved else None},
+                           "solved_in_timed_region": int(solved), "avg_children_per_step": nodes / args.steps / world,
+                           "avg_heuristic_rows_per_step": kept / args.steps, "mean_solution_len": (len_sum / solved) if solved else None},
                 "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                         "note": "BWASGpu.reset(host state)/step()/path_to() wall clock; the search never leaves HBM, only the start "
                                 "state goes in and counters/solution come out"},

@@ -49,13 +49,14 @@ template <int ENV, int M0, int G, class Sink> struct ExpandGroup {
   }
 };
 
-template <int ENV, int M0, class Sink> struct ExpandAll {
+template <int ENV, int M0, int M1, class Sink> struct ExpandRange {     // children M0 .. M1-1
   static DCB_DEV void run(const uint32_t (&p)[ExpandShape<ENV>::W], const uint32_t (&zm)[ExpandShape<ENV>::W],
                           uint64_t goal_hash, Sink &sink) {
     using Sh = ExpandShape<ENV>;
-    if constexpr (M0 < Sh::A) {
+    static_assert(M0 % Sh::GROUP == 0 && M1 % Sh::GROUP == 0, "move ranges are whole packing groups");
+    if constexpr (M0 < M1) {
       ExpandGroup<ENV, M0, Sh::GROUP, Sink>::run(p, zm, goal_hash, sink);
-      ExpandAll<ENV, M0 + Sh::GROUP, Sink>::run(p, zm, goal_hash, sink);
+      ExpandRange<ENV, M0 + Sh::GROUP, M1, Sink>::run(p, zm, goal_hash, sink);
     }
   }
 };
@@ -68,8 +69,9 @@ template <int ENV> DCB_DEV uint64_t goal_hash_value() {
   return state_hash<Sh::W>(g);
 }
 
-// p: aligned parent words (bytes >= S zero).
-template <int ENV, class Sink> DCB_DEV void expand_parent(const uint32_t (&p)[ExpandShape<ENV>::W], Sink &sink) {
+// p: aligned parent words (bytes >= S zero).  Children [M0, M1) only (default: all) -- lets several warps share a parent.
+template <int ENV, class Sink, int M0 = 0, int M1 = ExpandShape<ENV>::A>
+DCB_DEV void expand_parent(const uint32_t (&p)[ExpandShape<ENV>::W], Sink &sink) {
   using Sh = ExpandShape<ENV>;
   uint32_t zm[Sh::W];
   if constexpr (EnvTraits<ENV>::kPuzzle) {
@@ -79,7 +81,7 @@ template <int ENV, class Sink> DCB_DEV void expand_parent(const uint32_t (&p)[Ex
     for (int i = 0; i < Sh::W; i++) zm[i] = 0;
   }
   const uint64_t gh = goal_hash_value<ENV>();
-  ExpandAll<ENV, 0, Sink>::run(p, zm, gh, sink);
+  ExpandRange<ENV, M0, M1, Sink>::run(p, zm, gh, sink);
 }
 
 // One child for a runtime action (Environment.next_state).

@@ -13,14 +13,14 @@
 // 222-256), the OpenMP loop of parallel_weighted_astar.cpp:217-230, and Environment.expand/_move_np/
 // is_solved of environments/cube3.py:71-75,129-171 and environments/n_puzzle.py:78-82,136-231.
 #include <cuda_runtime.h>
+#include <stdlib.h>
+#include <string.h>
 #include "dcb_internal.h"
 #include "expand_core.cuh"
 #include "ptx.cuh"
 
 namespace dcb {
 
-constexpr int kExpandWarps = 4;
-constexpr int kExpandThreads = kExpandWarps * 32;
 
 // ---- vector stores of a run of record words into the lane's staging slot --------------------------
 template <int K0, int I, int N, int ALIGNW> struct StoreWords {
@@ -48,9 +48,9 @@ template <int ENV> struct SmemSink {
   static constexpr int ALIGNW = (Sh::REC_WORDS % 4 == 0) ? 4 : ((Sh::REC_WORDS % 2 == 0) ? 2 : 1);
   uint32_t *rec;
   uint64_t *hash_out;   // this parent's A hashes (16-byte aligned) or nullptr
-  uint32_t *solved_out; // this parent's A flags as words or nullptr
+  uint16_t *solved_out; // this parent's A flags as move pairs or nullptr
   uint64_t h_even;
-  uint32_t s_word;
+  uint32_t s_even;
 
   template <int K0, int N> __device__ __forceinline__ void store_record_words(const uint32_t (&r)[N]) {
     StoreWords<K0, 0, N, ALIGNW>::run(rec, r);
@@ -60,11 +60,8 @@ template <int ENV> struct SmemSink {
     else if (hash_out) stg_cs_v2u64(hash_out + MOVE - 1, h_even, h);
   }
   template <int MOVE> __device__ __forceinline__ void store_solved(bool s) {
-    if constexpr (MOVE % 4 == 0) s_word = 0;
-    s_word |= (s ? 1u : 0u) << (8 * (MOVE % 4));
-    if constexpr (MOVE % 4 == 3) {
-      if (solved_out) stg_cs_u32(solved_out + MOVE / 4, s_word);
-    }
+    if constexpr (MOVE % 2 == 0) s_even = s ? 1u : 0u;
+    else if (solved_out) solved_out[MOVE / 2] = (uint16_t)(s_even | ((s ? 1u : 0u) << 8));
   }
 };
 
@@ -74,56 +71,80 @@ template <int S> __device__ __forceinline__ void load_raw(const uint8_t *base, u
   for (int k = 0; k < LoadShape<S>::NRAW; k++) raw[k] = ldg_nc_u32(a + k);
 }
 
-template <int ENV, bool INDEXED>
-__global__ void __launch_bounds__(kExpandThreads)
+__device__ __forceinline__ void team_sync(int split, int team) {
+  if (split == 1) __syncwarp();
+  else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(32 * split) : "memory");
+}
+
+// TEAMS staging tiles per CTA, each filled by SPLIT warps: lane l of every warp of a team owns parent l of the tile and
+// warp `member` produces children [member*A/SPLIT, (member+1)*A/SPLIT).  Splitting the 12 moves over two warps halves
+// the time a tile spends being computed, so a larger share of the SM's staging memory is in flight to HBM at any time.
+template <int ENV, bool INDEXED, int TEAMS, int SPLIT>
+__global__ void __launch_bounds__(TEAMS * SPLIT * 32)
 expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids, int64_t n,
               uint8_t *__restrict__ children, uint8_t *__restrict__ solved, uint64_t *__restrict__ hash) {
   using Sh = ExpandShape<ENV>;
+  static_assert(Sh::A % (SPLIT * Sh::GROUP) == 0, "moves must split into whole packing groups");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int team = warp / SPLIT, member = warp % SPLIT;
   constexpr int kTileBytes = 32 * Sh::REC_BYTES;
-  uint8_t *tile_smem = smem_raw + warp * kTileBytes;
+  uint8_t *tile_smem = smem_raw + team * kTileBytes;
   uint32_t *lane_rec = reinterpret_cast<uint32_t *>(tile_smem) + lane * Sh::REC_WORDS;
+  const bool issuer = member == 0 && lane == 0;
 
   const int64_t n_tiles = (n + 31) >> 5;
-  const int64_t warp_stride = (int64_t)gridDim.x * kExpandWarps;
-  for (int64_t tile = (int64_t)blockIdx.x * kExpandWarps + warp; tile < n_tiles; tile += warp_stride) {
+  const int64_t tile_stride = (int64_t)gridDim.x * TEAMS;
+  // software pipeline: the parent words of the next tile are requested before this tile is computed
+  uint32_t raw_next[LoadShape<Sh::S>::NRAW];
+  uint64_t off_next = 0;
+  int64_t tile = (int64_t)blockIdx.x * TEAMS + team;
+  auto issue_loads = [&](int64_t t) {
+    const int64_t p = t * 32 + lane;
+    if (t < n_tiles && p < n) {
+      const uint64_t node = INDEXED ? (uint64_t)ids[p] : (uint64_t)p;
+      off_next = node * Sh::S;
+      load_raw<Sh::S>(src, off_next, raw_next);
+    }
+  };
+  issue_loads(tile);
+  for (; tile < n_tiles; tile += tile_stride) {
     const int64_t p = tile * 32 + lane;
     const bool valid = p < n;
-    // issue the parent loads before waiting on the previous tile's store: they do not touch smem
     uint32_t raw[LoadShape<Sh::S>::NRAW];
-    uint64_t off = 0;
-    if (valid) {
-      const uint64_t node = INDEXED ? (uint64_t)ids[p] : (uint64_t)p;
-      off = node * Sh::S;
-      load_raw<Sh::S>(src, off, raw);
-    }
-    if (lane == 0) bulk_wait_read_all();   // previous bulk store has drained this warp's staging tile
-    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < LoadShape<Sh::S>::NRAW; k++) raw[k] = raw_next[k];
+    const uint64_t off = off_next;
+    issue_loads(tile + tile_stride);
+    if (issuer) bulk_wait_read_all();      // the previous bulk store has drained this team's staging tile
+    team_sync(SPLIT, team);
     if (valid) {
       uint32_t w[Sh::W];
       align_state<Sh::S, Sh::W>(raw, (uint32_t)(off & 3), w);
       SmemSink<ENV> sink;
       sink.rec = lane_rec;
       sink.hash_out = hash ? hash + p * Sh::A : nullptr;
-      sink.solved_out = solved ? reinterpret_cast<uint32_t *>(solved + p * Sh::A) : nullptr;
-      expand_parent<ENV>(w, sink);
+      sink.solved_out = solved ? reinterpret_cast<uint16_t *>(solved + p * Sh::A) : nullptr;
+      constexpr int PER = Sh::A / SPLIT;
+      if constexpr (SPLIT == 1) expand_parent<ENV, SmemSink<ENV>, 0, Sh::A>(w, sink);
+      else if (member == 0) expand_parent<ENV, SmemSink<ENV>, 0, PER>(w, sink);
+      else expand_parent<ENV, SmemSink<ENV>, PER, 2 * PER>(w, sink);
     }
     fence_proxy_async_smem();
-    __syncwarp();
+    team_sync(SPLIT, team);
     const int64_t rem = n - tile * 32;
     const uint32_t bytes = (uint32_t)((rem < 32 ? rem : 32) * Sh::REC_BYTES);
     const uint32_t bulk = bytes & ~15u;
     uint8_t *gdst = children + tile * (int64_t)kTileBytes;
-    if (lane == 0 && bulk) {
+    if (issuer && bulk) {
       bulk_store_s2g(gdst, tile_smem, bulk);
       bulk_commit();
     }
     // a partial last tile can leave 4..12 trailing bytes that are not a 16-byte multiple
-    if (lane < ((bytes - bulk) >> 2))
+    if (member == 0 && lane < ((bytes - bulk) >> 2))
       reinterpret_cast<uint32_t *>(gdst + bulk)[lane] = reinterpret_cast<const uint32_t *>(tile_smem + bulk)[lane];
   }
-  if (lane == 0) bulk_wait_read_all();
+  if (issuer) bulk_wait_read_all();
 }
 
 // ---- secondary single-state kernels (Environment.next_state / is_solved / hash / nnet input) -------
@@ -199,27 +220,62 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int ENV, bool INDEXED>
-static int launch_expand(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
-                         uint64_t *hash, cudaStream_t st) {
+template <int ENV, bool INDEXED, int TEAMS, int SPLIT>
+static int launch_expand_cfg(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved, uint64_t *hash,
+                             cudaStream_t st) {
   using Sh = ExpandShape<ENV>;
-  if (n == 0) return DCB_OK;
-  constexpr int smem = kExpandWarps * 32 * Sh::REC_BYTES;
+  constexpr int smem = TEAMS * 32 * Sh::REC_BYTES;
+  constexpr int threads = TEAMS * SPLIT * 32;
   static bool configured = false;
   static int blocks_per_sm = 1;
-  auto kern = expand_kernel<ENV, INDEXED>;
+  auto kern = expand_kernel<ENV, INDEXED, TEAMS, SPLIT>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return dcb_cuda_fail();
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, kExpandThreads, smem) != cudaSuccess) return dcb_cuda_fail();
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem) != cudaSuccess) return dcb_cuda_fail();
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     configured = true;
   }
   const int64_t n_tiles = (n + 31) / 32;
-  int64_t blocks = (n_tiles + kExpandWarps - 1) / kExpandWarps;
+  int64_t blocks = (n_tiles + TEAMS - 1) / TEAMS;
   const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, kExpandThreads, smem, st>>>(src, ids, n, children, solved, hash);
+  kern<<<(unsigned)blocks, threads, smem, st>>>(src, ids, n, children, solved, hash);
   return dcb_check_launch();
+}
+
+// cube3 configuration: DCB_EXPAND_CFG="<teams>x<split>" picks an experimental shape (tools/sweep_expand.py)
+static int cube3_cfg() {
+  static int cfg = -1;
+  if (cfg < 0) {
+    const char *e = getenv("DCB_EXPAND_CFG");
+    cfg = 0;
+    if (e) {
+      if (!strcmp(e, "4x1")) cfg = 1;
+      else if (!strcmp(e, "5x1")) cfg = 2;
+      else if (!strcmp(e, "2x2")) cfg = 3;
+      else if (!strcmp(e, "5x2")) cfg = 4;
+      else if (!strcmp(e, "1x2")) cfg = 5;
+    }
+  }
+  return cfg;
+}
+
+template <int ENV, bool INDEXED>
+static int launch_expand(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
+                         uint64_t *hash, cudaStream_t st) {
+  if (n == 0) return DCB_OK;
+  if constexpr (ENV == 0) {
+    switch (cube3_cfg()) {
+      case 1: return launch_expand_cfg<0, INDEXED, 4, 1>(src, ids, n, children, solved, hash, st);
+      case 2: return launch_expand_cfg<0, INDEXED, 5, 1>(src, ids, n, children, solved, hash, st);
+      case 3: return launch_expand_cfg<0, INDEXED, 2, 2>(src, ids, n, children, solved, hash, st);
+      case 4: return launch_expand_cfg<0, INDEXED, 5, 2>(src, ids, n, children, solved, hash, st);
+      case 5: return launch_expand_cfg<0, INDEXED, 1, 2>(src, ids, n, children, solved, hash, st);
+      default: return launch_expand_cfg<0, INDEXED, 4, 1>(src, ids, n, children, solved, hash, st);
+    }
+  } else {
+    return launch_expand_cfg<ENV, INDEXED, 4, 1>(src, ids, n, children, solved, hash, st);
+  }
 }
 
 template <bool INDEXED>

@@ -113,6 +113,7 @@ class BWASGpu:
         self.h2d_bytes = 0
         self.d2h_bytes = 0
         self.expand_events = None           # list of (start, end, n_parents) CUDA events when profiling is on
+        self.total_kept = 0                 # children that survived CLOSED (= rows sent to the heuristic), all searches
 
     # ------------------------------------------------------------------------------------------------
     def _stream(self) -> int:
@@ -233,6 +234,7 @@ class BWASGpu:
             torch.cuda.current_stream(self.dev).synchronize()
             n_kept = int(self.h_counters[0]) & 0xFFFFFFFF
             self.last_kept = n_kept
+            self.total_kept += n_kept
             t3 = time.perf_counter(); tm["check"] += t3 - t2
             # ---- heuristic on the kept children only, same stream ----
             if n_kept:
