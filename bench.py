@@ -300,8 +300,10 @@ def reference_sample(steps: int, warmup: int, use_gpu_heuristic: bool = True):
     try:
         for s in states:
             stamps.clear()
+            # torchrun exports OMP_NUM_THREADS=1; the reference's OpenMP loops get every host thread, as in its own runs
+            child_env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
             p = subprocess.Popen([REF_BINARY, " ".join(str(int(v)) for v in s), str(WEIGHT), str(BATCH), srv.path, "cube3", "0"],
-                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                                 stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=child_env)
             # only full-batch iterations count as steps (the first ~6 requests of a search are the ramp-up)
             full = 0
             seen = 0

@@ -33,7 +33,8 @@ constexpr int W_TILE_BYTES = BN * BK * 2;              // 32 KB
 
 constexpr int STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES;   // one A tile + one W tile per pipeline stage (48 KB)
 constexpr int STAGES = 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int EPI_STAGE_BYTES = 4 * 8192;               // per epilogue warp: 32 rows x 128 B, fp16 hi and lo
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 constexpr int kMaxPairs = 3;
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------
@@ -136,7 +137,8 @@ __global__ void __launch_bounds__(kThreads, 1)
 resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueArgs ep, int64_t M, int Np, int Kp) {
   extern __shared__ uint8_t smem_dyn[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES);
+  uint8_t *ep_stage = smem + STAGES * STAGE_BYTES;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ep_stage + EPI_STAGE_BYTES);
   uint64_t *empty_bar = full_bar + STAGES;
   uint64_t *tmem_full = empty_bar + STAGES;          // [2]
   uint64_t *tmem_empty = tmem_full + 2;              // [2]
@@ -208,83 +210,99 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
     }
   } else {
     // ===================== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w%4) .. +31 =====================
+    // A thread owns one output row (TMEM lane); results leave through a per-warp XOR-swizzled shared-memory tile so that
+    // eight lanes write one full 128-byte line of a row (fp16 hi / lo) instead of 32 lanes writing 16-byte fragments.
     const int lane_grp = warp & 3;
+    uint8_t *stage_hi = ep_stage + (warp - 2) * 8192, *stage_lo = stage_hi + 4096;
     int buf = 0; uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const int64_t row = (t / n_tiles) * BM + lane_grp * 32 + lane;
+      const int64_t row0 = (t / n_tiles) * BM + lane_grp * 32;
+      const int64_t row = row0 + lane;
       const int n0 = (int)((t % n_tiles) * BN);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
       const bool row_ok = row < M;
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t acc[32];
-        tmem_ld_32x32(taddr + c, acc);
-        if (row_ok) {
-          const int64_t off = row * Np + n0 + c;
-          float v[32];
+      for (int c = 0; c < BN; c += 64) {
+        uint32_t acc0[32], acc1[32];
+        tmem_ld_32x32(taddr + c, acc0);
+        tmem_ld_32x32(taddr + c + 32, acc1);
+        float v[64];
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = __uint_as_float(acc[j]);
-          if (ep.partial_in) {
-            const float4 *pi = reinterpret_cast<const float4 *>(ep.partial_in + off);
+        for (int j = 0; j < 32; j++) { v[j] = __uint_as_float(acc0[j]); v[32 + j] = __uint_as_float(acc1[j]); }
+        const int64_t off = row * Np + n0 + c;
+        if (row_ok && ep.partial_in) {
+          const float4 *pi = reinterpret_cast<const float4 *>(ep.partial_in + off);
 #pragma unroll
-            for (int q = 0; q < 8; q++) { const float4 f = pi[q]; v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w; }
-          }
-          if (ep.partial_out) {
+          for (int q = 0; q < 16; q++) { const float4 f = pi[q]; v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w; }
+        }
+        if (ep.partial_out) {                        // K-chunk chaining: raw fp32 sums only (warp-uniform branch)
+          if (row_ok) {
             float4 *po = reinterpret_cast<float4 *>(ep.partial_out + off);
 #pragma unroll
-            for (int q = 0; q < 8; q++) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            continue;
+            for (int q = 0; q < 16; q++) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
           }
+          continue;
+        }
 #pragma unroll
-          for (int j = 0; j < 32; j++) v[j] = fmaf(v[j], ep.scale, __ldg(ep.bias + n0 + c + j));
-          if (ep.skip_hi) {
-            const uint4 *sh = reinterpret_cast<const uint4 *>(ep.skip_hi + off);
+        for (int j = 0; j < 64; j++) v[j] = fmaf(v[j], ep.scale, __ldg(ep.bias + n0 + c + j));
+        if (row_ok && ep.skip_hi) {
+          const uint4 *sh = reinterpret_cast<const uint4 *>(ep.skip_hi + off);
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 u = sh[q];
+          for (int q = 0; q < 8; q++) {
+            const uint4 u = sh[q];
+            const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); v[q * 8 + 2 * e] += f.x; v[q * 8 + 2 * e + 1] += f.y; }
+          }
+          if (ep.skip_lo) {
+            const uint4 *sl = reinterpret_cast<const uint4 *>(ep.skip_lo + off);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              const uint4 u = sl[q];
               const __half2 *h = reinterpret_cast<const __half2 *>(&u);
 #pragma unroll
               for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); v[q * 8 + 2 * e] += f.x; v[q * 8 + 2 * e + 1] += f.y; }
             }
-            if (ep.skip_lo) {
-              const uint4 *sl = reinterpret_cast<const uint4 *>(ep.skip_lo + off);
-#pragma unroll
-              for (int q = 0; q < 4; q++) {
-                const uint4 u = sl[q];
-                const __half2 *h = reinterpret_cast<const __half2 *>(&u);
-#pragma unroll
-                for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); v[q * 8 + 2 * e] += f.x; v[q * 8 + 2 * e + 1] += f.y; }
-              }
-            }
           }
-          if (ep.relu) {
+        }
+        if (ep.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = fmaxf(v[j], 0.0f);
-          }
-          if (ep.out_f32) {
-            float4 *o = reinterpret_cast<float4 *>(ep.out_f32 + off);
+          for (int j = 0; j < 64; j++) v[j] = fmaxf(v[j], 0.0f);
+        }
+        if (row_ok && ep.out_f32) {
+          float4 *o = reinterpret_cast<float4 *>(ep.out_f32 + off);
 #pragma unroll
-            for (int q = 0; q < 8; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          }
-          uint4 ph[4], pl[4];
-          __half2 *hh = reinterpret_cast<__half2 *>(ph), *ll = reinterpret_cast<__half2 *>(pl);
+          for (int q = 0; q < 16; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+        // fp16 hi / lo split, staged (chunk q of row `lane` lives at 16-byte slot q ^ (lane & 7): conflict-free both ways)
+        __syncwarp();                                  // the previous slice has been read out of the staging tile
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            const float a = fminf(fmaxf(v[2 * j], -65504.0f), 65504.0f), b = fminf(fmaxf(v[2 * j + 1], -65504.0f), 65504.0f);
+        for (int q = 0; q < 8; q++) {
+          uint4 ph, pl;
+          __half2 *hh = reinterpret_cast<__half2 *>(&ph), *ll = reinterpret_cast<__half2 *>(&pl);
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float a = fminf(fmaxf(v[8 * q + 2 * e], -65504.0f), 65504.0f), b = fminf(fmaxf(v[8 * q + 2 * e + 1], -65504.0f), 65504.0f);
             const __half2 h = __floats2half2_rn(a, b);
             const float2 hf = __half22float2(h);
-            hh[j] = h;
-            ll[j] = __floats2half2_rn(a - hf.x, b - hf.y);
+            hh[e] = h;
+            ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
           }
-          uint4 *oh = reinterpret_cast<uint4 *>(ep.out_hi + off);
+          const int slot = ((q ^ (lane & 7)) << 4) + lane * 128;
+          *reinterpret_cast<uint4 *>(stage_hi + slot) = ph;
+          *reinterpret_cast<uint4 *>(stage_lo + slot) = pl;
+        }
+        __syncwarp();
 #pragma unroll
-          for (int q = 0; q < 4; q++) oh[q] = ph[q];
-          if (ep.out_lo) {
-            uint4 *ol = reinterpret_cast<uint4 *>(ep.out_lo + off);
-#pragma unroll
-            for (int q = 0; q < 4; q++) ol[q] = pl[q];
+        for (int i = 0; i < 8; i++) {
+          const int r = 4 * i + (lane >> 3), ch = lane & 7;
+          const int slot = ((ch ^ (r & 7)) << 4) + r * 128;
+          if (row0 + r < M) {
+            const int64_t o = (row0 + r) * Np + n0 + c + ch * 8;
+            *reinterpret_cast<uint4 *>(ep.out_hi + o) = *reinterpret_cast<const uint4 *>(stage_hi + slot);
+            if (ep.out_lo) *reinterpret_cast<uint4 *>(ep.out_lo + o) = *reinterpret_cast<const uint4 *>(stage_lo + slot);
           }
         }
       }

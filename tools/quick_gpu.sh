@@ -1,15 +1,8 @@
 cd $GRAFT_REPO_ROOT
-python - <<'PY'
-import torch
-t = torch.empty(1 << 31, dtype=torch.uint8, device="cuda")
-for name, fn in (("fill (write only)", lambda: t.fill_(3)), ("copy (read+write)", lambda: t[: 1 << 30].copy_(t[1 << 30:]))):
-    for _ in range(3): fn()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(10): fn()
-    b.record(); torch.cuda.synchronize()
-    ms = a.elapsed_time(b) / 10
-    print("%-20s %.1f GB/s" % (name, (2 ** 31) / ms / 1e6))
-PY
-python tools/validate_quality.py puzzle15 40 fp16x3 2>&1 | tail -10
-python tools/validate_quality.py cube3 100 fp16x3 2>&1 | tail -10
+nvidia-smi --query-gpu=index,name --format=csv,noheader
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29531 bench.py --gpus 2 --steps 30 --warmup 6 --no_cpu_baseline 2>gpurun_out/bench_2gpu.err | tee gpurun_out/bench_2gpu.json | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('N=2 value %.4g ms/step %.2f e2e %.4g n_gpus %d scaling %s' % (d['value'], d['ms_per_step'], d['e2e']['value'], d['n_gpus'], d['scaling']))"
+tail -3 gpurun_out/bench_2gpu.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29532 bench.py --impl reference --gpus 2 --steps 3 --warmup 1 2>/dev/null | cut -c1-160
+python bench.py --steps 30 --warmup 6 --no_cpu_baseline 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().split('\n')[-1]); print('N=1 value %.4g ms/step %.2f e2e %.4g' % (d['value'], d['ms_per_step'], d['e2e']['value']))"
