@@ -35,14 +35,16 @@ UNIT = "nodes/s"
 WEIGHT, BATCH = 0.8, 20000
 ALG_BYTES_PER_CHILD = 54.0 / 12 + 54 + 1 + 8          # expand + is_solved + hash, unpadded
 WEIGHTS = os.path.join(ROOT, "assets", "saved_models", "cube3", "current", "model_state_dict.pt")
+NCU_TRAFFIC_BYTES = 116.28e6 + 1527.19e6               # ncu --set full, expand_kernel<cube3>, 2^21 parents (profiles/expand_r01_ncu.txt)
 
 
 def measured_peaks():
+    """(HBM GB/s, bf16 TFLOP/s sustained, bf16 TFLOP/s burst, source)"""
     try:
         p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops_sustained", 1400.0)), float(p.get("bf16_tflops", 1590.0)), "measured (MEASURED_PEAKS.json)"
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return 6650.0, 1400.0, 1590.0, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -164,6 +166,10 @@ def run_ours(args):
     run_steps(args.warmup, cursor)
     # ---- device-resident timed region ----------------------------------------------------------------
     eng.expand_events = []
+    tc_heur = hasattr(heur, "gemm_events")
+    if tc_heur:
+        heur.gemm_events = []
+        gemm0 = heur.gemm_launches
     launches0 = eng.kernel_launches
     kept0 = eng.total_kept
     sampler = ClockSampler(local); sampler.start()
@@ -182,6 +188,12 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
     kept = eng.total_kept - kept0
+    gemm_ev = []
+    if tc_heur:
+        gemm_ev = [(a.elapsed_time(b), f) for a, b, f in heur.gemm_events]
+        heur.gemm_events = None
+        n_nn = heur.gemm_launches - gemm0
+        launches += n_nn + 2 * max(1, n_nn // 14)          # + one-hot and fc_out kernels of each forward pass
     in_loop = [(a.elapsed_time(b), n) for a, b, n in eng.expand_events]
     eng.expand_events = None
     # ---- end-to-end through the public API: host start state in, host solution out ---------------------
@@ -195,8 +207,22 @@ def run_ours(args):
     barrier()
     h2d, d2h = eng.h2d_bytes - h2d0, eng.d2h_bytes - d2h0
     # ---- gather-kernel roofline: streaming-size launches of the same kernel, CUDA events ------------------
-    peak, peak_src = measured_peaks()
+    peak, tc_sus, tc_burst, peak_src = measured_peaks()
     roof = None
+    roof_dom = None
+    if rank == 0 and gemm_ev:
+        # the dominant kernel of the step (95% of device time, profiles/launches_r01_summary.txt): the tcgen05 dense layers
+        t_s = sum(x[0] for x in gemm_ev) * 1e-3
+        fl = sum(x[1] for x in gemm_ev)
+        ach = fl / t_s / 1e12
+        roof_dom = {"kernel": "resnet_gemm_kernel (tcgen05 dense layers of the cost-to-go ResNet)", "bound": "tensor", "achieved": round(ach, 1),
+                    "peak": tc_sus, "unit": "TFLOP/s", "frac": round(ach / tc_sus, 4), "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % tc_burst,
+                    "launches": len(gemm_ev), "avg_us": round(t_s / len(gemm_ev) * 1e6, 1), "share_of_timed_region": round(t_s * 1e3 / ms, 4),
+                    "algorithmic_flops": "2*rows*N*K of the unpadded layer (29.24 MFLOP per cube3 state, SURVEY 8d), one product",
+                    "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 2e-5 vs fp64) "
+                            "on tiles padded to 256x64; executed tensor work = %.0f TFLOP/s; ncu: tensor pipe active 74-81%% (profiles/resnet_gemm_r01_ncu.txt)"
+                            % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1",
+                               ach * (89.7 / 29.24 if args.nnet_precision == "fp16x3" else 29.9 / 29.24))}
     if rank == 0:
         n_par = 1 << 21
         g = torch.Generator(device=dev); g.manual_seed(0)
@@ -213,7 +239,9 @@ def run_ours(args):
         t = float(np.mean(times)) * 1e-3
         ach = ALG_BYTES_PER_CHILD * n_par * 12 / t / 1e9
         roof = {"kernel": "expand_kernel<cube3> (expand+is_solved+hash)", "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
-                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/expand_r01_ncu.txt "
+                                  "(algorithmic bytes per launch: %.4g)" % (ALG_BYTES_PER_CHILD * n_par * 12),
                 "launch": "%d parents -> %d children, outputs 1.7 GB > L2" % (n_par, n_par * 12),
                 "alg_bytes_per_child": ALG_BYTES_PER_CHILD, "children_per_sec": round(n_par * 12 / t, 1)}
         if in_loop:
@@ -254,7 +282,10 @@ def run_ours(args):
                 "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
                         "note": "BWASGpu.reset(host state)/step()/path_to() wall clock; the search never leaves HBM, only the start "
                                 "state goes in and counters/solution come out"},
-                "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}
+                "gpu_launches": int(launches), "clocks": clocks,
+                "roofline": roof_dom if roof_dom is not None else roof,      # dominant kernel of the step
+                "roofline_gather": roof,                                      # BASELINE.json: "gather-kernel HBM GB/s vs roofline"
+                "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -72,7 +72,9 @@ class TcResnet:
         self.k0 = self.layers[0].kp
         assert self.layers[0].k == self.state_dim * self.depth
         self._bufs = {}
-        self.flops_per_row = sum(2 * l.np_ * l.kp for l in self.layers)
+        self.flops_per_row = sum(2 * l.n * l.k for l in self.layers)           # algorithmic (unpadded, one product): 29.24 MFLOP for cube3
+        self.gemm_events = None     # when a list: (start_event, end_event, algorithmic_flops) per dcb_resnet_gemm launch (bench.py)
+        self.gemm_launches = 0
 
     def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols)
@@ -95,11 +97,17 @@ class TcResnet:
             k0 = c * chunk
             kc = min(chunk, layer.kp - k0)
             last = c == n_chunks - 1
+            self.gemm_launches += 1
+            if self.gemm_events is not None:
+                ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
             check(lib.dcb_resnet_gemm(a_hi.data_ptr() + 2 * k0, (a_lo.data_ptr() + 2 * k0) if use_lo else None, lda,
                                       layer.w_hi.data_ptr() + 2 * k0, (layer.w_lo.data_ptr() + 2 * k0) if layer.w_lo is not None else None, ldw,
                                       ptr(layer.bias), layer.scale, ptr(skip_hi) if last else None, ptr(skip_lo) if last else None,
                                       1 if relu else 0, ptr(out_hi), ptr(out_lo), None,
                                       ptr(part) if c > 0 else None, None if last else ptr(part), m, layer.np_, kc, st), "dcb_resnet_gemm")
+            if self.gemm_events is not None:
+                ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+                self.gemm_events.append((ev0, ev1, 2.0 * m * layer.n * min(kc, max(layer.k - k0, 0))))
 
     def _buf32(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols, 32)
