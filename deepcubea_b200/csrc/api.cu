@@ -36,6 +36,7 @@ int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const vo
                        float scale, const void *skip_hi, const void *skip_lo, int relu, void *out_hi, void *out_lo, float *out_f32,
                        const float *partial_in, float *partial_out, int64_t M, int Np, int Kp, cudaStream_t st);
 int onehot_device(const uint8_t *x, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
+int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
 int rowdot_device(const void *x_hi, const void *x_lo, const float *w, float bias, int64_t M, int n_valid, int ld, float *out, cudaStream_t st);
 int path_device(const uint32_t *slot_parent, uint32_t goal_id, int A, int32_t max_len, uint8_t *moves, int32_t *len, cudaStream_t st);
 }  // namespace dcb
@@ -315,9 +316,18 @@ int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int3
   if (!aligned16(d_out)) return DCB_ERR_ALIGN;
   return onehot_device(d_nnet_in, m, state_dim, depth, k_padded, d_out, S(stream));
 }
+int dcb_onehot_fp16_nodes(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, int32_t depth, int32_t k_padded, void *d_out,
+                          void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  const int s = kStateBytes[env];
+  if (m < 0 || depth <= 0 || k_padded < s * depth || k_padded % 64 || (m > 0 && (!d_arena || !d_ids || !d_out))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_out)) return DCB_ERR_ALIGN;
+  return onehot_gather_device(env, d_arena, d_ids, m, s, depth, k_padded, d_out, S(stream));
+}
 int dcb_rowdot(const void *d_x_hi, const void *d_x_lo, const float *d_w, float bias, int64_t m, int32_t n_valid, int32_t ld, float *d_out,
                void *stream) {
-  if (m < 0 || n_valid <= 0 || ld < n_valid || (ld & 1) || (m > 0 && (!d_x_hi || !d_w || !d_out))) return DCB_ERR_BAD_ARG;
+  if (m < 0 || n_valid <= 0 || ld < n_valid || (ld & 7) || (m > 0 && (!d_x_hi || !d_w || !d_out))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_x_hi) || !aligned16(d_x_lo)) return DCB_ERR_ALIGN;
   return rowdot_device(d_x_hi, d_x_lo, d_w, bias, m, n_valid, ld, d_out, S(stream));
 }
 

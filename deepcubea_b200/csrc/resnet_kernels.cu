@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include "dcb_internal.h"
 
 namespace dcb {
@@ -66,6 +67,54 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap *map, uint64_t *ba
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
                    smem_addr(dst)),
                "l"(map), "r"(smem_addr(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` in CTA `rank` of this cluster
+__device__ __forceinline__ uint32_t map_to_cta(const void *p, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr(p)), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion bytes are credited to the mbarrier of the LEADER CTA of the pair (bit 24 of a shared::cluster
+// address selects the CTA within the pair)
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap *map, uint32_t leader_bar_cluster_addr, void *dst, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_addr(dst)),
+      "l"(map), "r"(leader_bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t *smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_addr(smem_dst)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive (once all MMAs issued so far have retired) on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_addr(bar)),
+               "h"((uint16_t)0x3)
                : "memory");
 }
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t cols) {
@@ -132,6 +181,97 @@ struct PairMaps {              // operand pairs, swept in order; the last one is
   CUtensorMap a[kMaxPairs];
   CUtensorMap w[kMaxPairs];
 };
+
+// One accumulator tile (this warp's 32 TMEM lanes x 256 columns) -> global memory.  A thread owns one output row; results
+// leave through a per-warp XOR-swizzled shared-memory tile so that eight lanes write one full 128-byte line of a row.
+__device__ __forceinline__ void epilogue_tile(const EpilogueArgs &ep, uint32_t taddr, int64_t row0, int n0, int64_t M, int Np, int lane,
+                                              uint8_t *stage_hi, uint8_t *stage_lo) {
+  const int64_t row = row0 + lane;
+      const bool row_ok = row < M;
+#pragma unroll 1
+for (int c = 0; c < BN; c += 64) {
+  uint32_t acc0[32], acc1[32];
+  tmem_ld_32x32(taddr + c, acc0);
+  tmem_ld_32x32(taddr + c + 32, acc1);
+  float v[64];
+#pragma unroll
+  for (int j = 0; j < 32; j++) { v[j] = __uint_as_float(acc0[j]); v[32 + j] = __uint_as_float(acc1[j]); }
+  const int64_t off = row * Np + n0 + c;
+  if (row_ok && ep.partial_in) {
+    const float4 *pi = reinterpret_cast<const float4 *>(ep.partial_in + off);
+#pragma unroll
+    for (int q = 0; q < 16; q++) { const float4 f = pi[q]; v[4 * q] += f.x; v[4 * q + 1] += f.y; v[4 * q + 2] += f.z; v[4 * q + 3] += f.w; }
+  }
+  if (ep.partial_out) {                        // K-chunk chaining: raw fp32 sums only (warp-uniform branch)
+    if (row_ok) {
+      float4 *po = reinterpret_cast<float4 *>(ep.partial_out + off);
+#pragma unroll
+      for (int q = 0; q < 16; q++) po[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    continue;
+  }
+#pragma unroll
+  for (int j = 0; j < 64; j++) v[j] = fmaf(v[j], ep.scale, __ldg(ep.bias + n0 + c + j));
+  if (row_ok && ep.skip_hi) {
+    const uint4 *sh = reinterpret_cast<const uint4 *>(ep.skip_hi + off);
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const uint4 u = sh[q];
+      const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+      for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); v[q * 8 + 2 * e] += f.x; v[q * 8 + 2 * e + 1] += f.y; }
+    }
+    if (ep.skip_lo) {
+      const uint4 *sl = reinterpret_cast<const uint4 *>(ep.skip_lo + off);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint4 u = sl[q];
+        const __half2 *h = reinterpret_cast<const __half2 *>(&u);
+#pragma unroll
+        for (int e = 0; e < 4; e++) { const float2 f = __half22float2(h[e]); v[q * 8 + 2 * e] += f.x; v[q * 8 + 2 * e + 1] += f.y; }
+      }
+    }
+  }
+  if (ep.relu) {
+#pragma unroll
+    for (int j = 0; j < 64; j++) v[j] = fmaxf(v[j], 0.0f);
+  }
+  if (row_ok && ep.out_f32) {
+    float4 *o = reinterpret_cast<float4 *>(ep.out_f32 + off);
+#pragma unroll
+    for (int q = 0; q < 16; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+  // fp16 hi / lo split, staged (chunk q of row `lane` lives at 16-byte slot q ^ (lane & 7): conflict-free both ways)
+  __syncwarp();                                  // the previous slice has been read out of the staging tile
+#pragma unroll
+  for (int q = 0; q < 8; q++) {
+    uint4 ph, pl;
+    __half2 *hh = reinterpret_cast<__half2 *>(&ph), *ll = reinterpret_cast<__half2 *>(&pl);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float a = fminf(fmaxf(v[8 * q + 2 * e], -65504.0f), 65504.0f), b = fminf(fmaxf(v[8 * q + 2 * e + 1], -65504.0f), 65504.0f);
+      const __half2 h = __floats2half2_rn(a, b);
+      const float2 hf = __half22float2(h);
+      hh[e] = h;
+      ll[e] = __floats2half2_rn(a - hf.x, b - hf.y);
+    }
+    const int slot = ((q ^ (lane & 7)) << 4) + lane * 128;
+    *reinterpret_cast<uint4 *>(stage_hi + slot) = ph;
+    *reinterpret_cast<uint4 *>(stage_lo + slot) = pl;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int r = 4 * i + (lane >> 3), ch = lane & 7;
+    const int slot = ((ch ^ (r & 7)) << 4) + r * 128;
+    if (row0 + r < M) {
+      const int64_t o = (row0 + r) * Np + n0 + c + ch * 8;
+      *reinterpret_cast<uint4 *>(ep.out_hi + o) = *reinterpret_cast<const uint4 *>(stage_hi + slot);
+      if (ep.out_lo) *reinterpret_cast<uint4 *>(ep.out_lo + o) = *reinterpret_cast<const uint4 *>(stage_lo + slot);
+    }
+  }
+}
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueArgs ep, int64_t M, int Np, int Kp) {
@@ -217,11 +357,11 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
     int buf = 0; uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int64_t row0 = (t / n_tiles) * BM + lane_grp * 32;
-      const int64_t row = row0 + lane;
       const int n0 = (int)((t % n_tiles) * BN);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
+      const int64_t row = row0 + lane;
       const bool row_ok = row < M;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64) {
@@ -317,6 +457,127 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// =====================================================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  Each CTA stages its own 128
+// A rows and HALF of the W tile (128 of the 256 N rows); the pair MMA (M = 256) issued by the leader reads both halves,
+// so a CTA stages 32 KB instead of 48 KB per four MMAs -- a third more MMA time per staged byte, which is what bounds the
+// single-CTA kernel (its 4 x 48 KB pipeline covers ~1 us of MMA work against ~1.4 us of load latency).
+// Barriers: full[s] lives in the LEADER (its arrive.expect_tx covers both CTAs' bytes; both CTAs' TMA loads credit it), empty[s] and tmem_full[b] are signalled in both CTAs by the leader's multicast commits,
+// tmem_empty[b] (leader) collects the 2 x 4 epilogue warps of both CTAs.
+// =====================================================================================================================
+constexpr int P_STAGE_BYTES = A_TILE_BYTES + W_TILE_BYTES / 2;      // 32 KB per CTA
+constexpr int P_STAGES = 6;
+constexpr int P_SMEM_BYTES = P_STAGES * P_STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t kIdescPair = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+resnet_gemm_pair_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueArgs ep, int64_t M, int Np, int Kp) {
+  extern __shared__ uint8_t smem_dyn[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  uint8_t *ep_stage = smem + P_STAGES * P_STAGE_BYTES;
+  uint64_t *full_bar = reinterpret_cast<uint64_t *>(ep_stage + EPI_STAGE_BYTES);
+  uint64_t *empty_bar = full_bar + P_STAGES;
+  uint64_t *tmem_full = empty_bar + P_STAGES;        // [2]
+  uint64_t *tmem_empty = tmem_full + 2;              // [2]
+  uint32_t *tmem_base_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int n_tiles = Np / BN, k_blocks = Kp / BK;
+  const int64_t m_pairs = (M + 2 * BM - 1) / (2 * BM);
+  const int64_t total_tiles = m_pairs * n_tiles;
+  const int64_t tile_first = blockIdx.x >> 1, tile_step = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < P_STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int b = 0; b < 2; b++) { mbar_init(&tmem_full[b], 1); mbar_init(&tmem_empty[b], 8); }   // 4 epilogue warps x 2 CTAs
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_pair(tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t leader_full0 = map_to_cta(&full_bar[0], 0);
+      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+        const int32_t m0 = (int32_t)((2 * (t / n_tiles) + rank) * BM), n0 = (int32_t)((t % n_tiles) * BN + rank * (BN / 2));
+        for (int p = 0; p < n_pairs; p++) {
+          for (int kb = 0; kb < k_blocks; kb++) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);                         // own stage buffer is free (leader's commit reaches both CTAs)
+            uint8_t *st = smem + stage * P_STAGE_BYTES;
+            // bytes of both CTAs land on the leader's barrier.  The peer does not arrive on it: a release-arrive across
+            // the cluster costs its producer ~0.5 us per stage (ncu: 43% of that warp's samples in the fence) and the
+            // leader's own arrive.expect_tx already keeps the phase open until every byte is in.
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * P_STAGE_BYTES);
+            tma_load_2d_pair(&maps.a[p], leader_full0 + 8u * (uint32_t)stage, st, kb * BK, m0);
+            tma_load_2d_pair(&maps.w[p], leader_full0 + 8u * (uint32_t)stage, st + A_TILE_BYTES, kb * BK, n0);
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: one thread of the leader CTA =====================
+    if (leader && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int buf = 0; uint32_t acc_phase = 0;
+      for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+        mbar_wait(&tmem_empty[buf], acc_phase ^ 1);            // both CTAs' epilogues have drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_acc = tmem_base + (uint32_t)buf * BN;
+        uint32_t first = 1;
+        for (int p = 0; p < n_pairs; p++) {
+          for (int kb = 0; kb < k_blocks; kb++) {
+            mbar_wait(&full_bar[stage], phase);
+            tc_fence_after();
+            const uint32_t st = smem_addr(smem + stage * P_STAGE_BYTES);
+            const uint64_t da = make_smem_desc(st), dw = make_smem_desc(st + A_TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; k++) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);
+              umma_f16_pair(tmem_acc, da + koff, dw + koff, kIdescPair, first ? 0u : 1u);
+              first = 0;
+            }
+            umma_commit_pair(&empty_bar[stage]);                // stage free in both CTAs once these MMAs retire
+            if (++stage == P_STAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit_pair(&tmem_full[buf]);                      // accumulators of both CTAs complete
+        if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue (both CTAs, own 128 rows each) =====================
+    const int lane_grp = warp & 3;
+    uint8_t *stage_hi = ep_stage + (warp - 2) * 8192, *stage_lo = stage_hi + 4096;
+    const uint32_t leader_tmem_empty0 = map_to_cta(&tmem_empty[0], 0);
+    int buf = 0; uint32_t acc_phase = 0;
+    for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
+      const int64_t row0 = (2 * (t / n_tiles) + rank) * BM + lane_grp * 32;
+      const int n0 = (int)((t % n_tiles) * BN);
+      mbar_wait(&tmem_full[buf], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
+      epilogue_tile(ep, taddr, row0, n0, M, Np, lane, stage_hi, stage_lo);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(leader_tmem_empty0 + 8u * (uint32_t)buf);
+      if (++buf == 2) { buf = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem_base, kTmemCols);
+}
+
 // ---- small kernels around the GEMMs ------------------------------------------------------------------
 // one-hot encoding of the nnet input (pytorch_models.py:49-52) as an fp16 matrix [M][Kp], K index = s*depth + value
 __global__ void __launch_bounds__(256) onehot_kernel(const uint8_t *__restrict__ x, int64_t M, int S, int depth, int Kp, __half *__restrict__ out) {
@@ -334,18 +595,48 @@ __global__ void __launch_bounds__(256) onehot_kernel(const uint8_t *__restrict__
   }
 }
 
-// fc_out (pytorch_models.py:85): out[m] = sum_n (hi+lo)[m][n] * w[n] + b, one warp per row, fp32
+// same, reading the states of the listed nodes straight from the search's node arena (state of node i at arena + i*S):
+// state_to_nnet_input (cube3.py:77-85: sticker / 9 -> colour) and F.one_hot in one pass, no intermediate u8 matrix
+template <bool DIV9>
+__global__ void __launch_bounds__(256) onehot_gather_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ ids, int64_t M, int S,
+                                                            int depth, int Kp, __half *__restrict__ out) {
+  const int64_t total = M * (int64_t)(Kp / 8);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / (Kp / 8);
+    const int k0 = (int)(i - m * (Kp / 8)) * 8;
+    const uint8_t *st = arena + (uint64_t)ids[m] * S;
+    __half h[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+      const int k = k0 + e, s = k / depth, v = k - s * depth;
+      int x = -1;
+      if (s < S) { x = st[s]; if (DIV9) x = (x * 57) >> 9; }
+      h[e] = (x == v) ? __float2half(1.0f) : __float2half(0.0f);
+    }
+    *reinterpret_cast<uint4 *>(out + m * Kp + k0) = *reinterpret_cast<const uint4 *>(h);
+  }
+}
+
+// fc_out (pytorch_models.py:85): out[m] = sum_n (hi+lo)[m][n] * w[n] + b, one warp per row, fp32.  Each lane reads 16 bytes
+// (8 halves) of hi and lo per step; the summation order is fixed, so results are reproducible run to run.
 __global__ void __launch_bounds__(256) rowdot_kernel(const __half *__restrict__ x_hi, const __half *__restrict__ x_lo, const float *__restrict__ w,
                                                      float bias, int64_t M, int n_valid, int ld, float *__restrict__ out) {
   const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= M) return;
   float acc = 0.0f;
-  for (int n = lane * 2; n < n_valid; n += 64) {
-    float2 f = __half22float2(*reinterpret_cast<const __half2 *>(x_hi + row * ld + n));
-    if (x_lo) { const float2 g = __half22float2(*reinterpret_cast<const __half2 *>(x_lo + row * ld + n)); f.x += g.x; f.y += g.y; }
-    acc = fmaf(f.x, w[n], acc);
-    if (n + 1 < n_valid) acc = fmaf(f.y, w[n + 1], acc);
+  for (int n = lane * 8; n < n_valid; n += 256) {              // ld is a multiple of 8 and rows are 16-byte aligned
+    const uint4 uh = *reinterpret_cast<const uint4 *>(x_hi + row * ld + n);
+    uint4 ul = make_uint4(0, 0, 0, 0);
+    if (x_lo) ul = *reinterpret_cast<const uint4 *>(x_lo + row * ld + n);
+    const __half2 *hh = reinterpret_cast<const __half2 *>(&uh), *hl = reinterpret_cast<const __half2 *>(&ul);
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const float2 f = __half22float2(hh[e]), g = __half22float2(hl[e]);
+      const int k = n + 2 * e;
+      if (k < n_valid) acc = fmaf(f.x + g.x, w[k], acc);
+      if (k + 1 < n_valid) acc = fmaf(f.y + g.y, w[k + 1], acc);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -387,10 +678,14 @@ int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const vo
                        const float *partial_in, float *partial_out, int64_t M, int Np, int Kp, cudaStream_t st) {
   if (M == 0) return DCB_OK;
   if (Np % BN || Kp % BK) return DCB_ERR_BAD_ARG;
+  // DCB_GEMM_PAIR=1 selects the CTA-pair (cta_group::2) kernel
+  static int use_pair = -1;
+  if (use_pair < 0) { const char *e = getenv("DCB_GEMM_PAIR"); use_pair = (e && e[0] == '1') ? 1 : 0; }
+  const int w_box = use_pair ? BN / 2 : BN;
   CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
-  if (!make_map(&ma_hi, a_hi, M, Kp, lda, BM) || !make_map(&mw_hi, w_hi, Np, Kp, ldw, BN)) return DCB_ERR_CUDA;
+  if (!make_map(&ma_hi, a_hi, M, Kp, lda, BM) || !make_map(&mw_hi, w_hi, Np, Kp, ldw, w_box)) return DCB_ERR_CUDA;
   if (a_lo && !make_map(&ma_lo, a_lo, M, Kp, lda, BM)) return DCB_ERR_CUDA;
-  if (w_lo && !make_map(&mw_lo, w_lo, Np, Kp, ldw, BN)) return DCB_ERR_CUDA;
+  if (w_lo && !make_map(&mw_lo, w_lo, Np, Kp, ldw, w_box)) return DCB_ERR_CUDA;
   PairMaps maps;
   int n = 0;
   if (w_lo) { maps.a[n] = ma_hi; maps.w[n] = mw_lo; n++; }                 // small products first
@@ -403,10 +698,17 @@ int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const vo
   static int sms = 148;
   if (!configured) {
     if (cudaFuncSetAttribute(resnet_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) return dcb_cuda_fail();
+    if (cudaFuncSetAttribute(resnet_gemm_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES) != cudaSuccess) return dcb_cuda_fail();
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
+  }
+  if (use_pair) {
+    const int64_t pair_tiles = ((M + 2 * BM - 1) / (2 * BM)) * (Np / BN);
+    const int64_t pairs = pair_tiles < sms / 2 ? pair_tiles : sms / 2;
+    resnet_gemm_pair_kernel<<<(unsigned)(2 * pairs), kThreads, P_SMEM_BYTES, st>>>(maps, n, ep, M, Np, Kp);
+    return dcb_check_launch();
   }
   const int64_t tiles = ((M + BM - 1) / BM) * (Np / BN);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
@@ -419,6 +721,15 @@ int onehot_device(const uint8_t *x, int64_t M, int S, int depth, int Kp, void *o
   int64_t blocks = (M * (Kp / 8) + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   onehot_kernel<<<(unsigned)blocks, 256, 0, st>>>(x, M, S, depth, Kp, (__half *)out);
+  return dcb_check_launch();
+}
+
+int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st) {
+  if (M == 0) return DCB_OK;
+  int64_t blocks = (M * (Kp / 8) + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  if (env == 0) onehot_gather_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
+  else onehot_gather_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
   return dcb_check_launch();
 }
 

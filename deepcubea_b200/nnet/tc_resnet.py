@@ -119,16 +119,28 @@ class TcResnet:
 
     @torch.no_grad()
     def __call__(self, x: torch.Tensor) -> torch.Tensor:
+        """nnet-input u8 [m, S] on the device -> cost-to-go f32 [m]."""
         assert x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and x.shape[1] == self.state_dim
-        n = x.shape[0]
+        return self._forward(x.shape[0], x=x)
+
+    @torch.no_grad()
+    def eval_nodes(self, env_id: int, arena: torch.Tensor, ids: torch.Tensor, n: int) -> torch.Tensor:
+        """Cost-to-go of nodes `ids[:n]` of a search arena: the one-hot input is built straight from the arena
+        (dcb_onehot_fp16_nodes), skipping the intermediate nnet-input matrix."""
+        return self._forward(n, env_id=env_id, arena=arena, ids=ids)
+
+    def _forward(self, n: int, x=None, env_id: int = 0, arena=None, ids=None) -> torch.Tensor:
         out = torch.empty(n, dtype=torch.float32, device=self.dev)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         sp = self.split
         for i0 in range(0, n, self.chunk):
             m = min(self.chunk, n - i0)
-            xin = x[i0:i0 + m]
             a0 = self._buf("onehot", m, self.k0)
-            check(self.lib.dcb_onehot_fp16(ptr(xin), m, self.state_dim, self.depth, self.k0, ptr(a0), st), "dcb_onehot_fp16")
+            if x is not None:
+                check(self.lib.dcb_onehot_fp16(ptr(x[i0:i0 + m]), m, self.state_dim, self.depth, self.k0, ptr(a0), st), "dcb_onehot_fp16")
+            else:
+                check(self.lib.dcb_onehot_fp16_nodes(env_id, ptr(arena), ids.data_ptr() + 4 * i0, m, self.depth, self.k0, ptr(a0), st),
+                      "dcb_onehot_fp16_nodes")
             l0, l1 = self.layers[0], self.layers[1]
             h1_hi = self._buf("h1_hi", m, l0.np_)
             h1_lo = self._buf("h1_lo", m, l0.np_) if sp else None

@@ -238,8 +238,11 @@ class BWASGpu:
             t3 = time.perf_counter(); tm["check"] += t3 - t2
             # ---- heuristic on the kept children only, same stream ----
             if n_kept:
-                check(lib.dcb_gather_nnet_input(env, ptr(self.arena), ptr(self.kept_ids), n_kept, ptr(self.nn_in), st), "gather_nnet_input")
-                h = self.heuristic(self.nn_in[:n_kept])
+                if hasattr(self.heuristic, "eval_nodes"):       # tcgen05 path: one-hot input built straight from the arena
+                    h = self.heuristic.eval_nodes(env, self.arena, self.kept_ids, n_kept)
+                else:
+                    check(lib.dcb_gather_nnet_input(env, ptr(self.arena), ptr(self.kept_ids), n_kept, ptr(self.nn_in), st), "gather_nnet_input")
+                    h = self.heuristic(self.nn_in[:n_kept])
                 if h.dtype != torch.float32 or not h.is_contiguous():
                     h = h.float().contiguous()
                 check(lib.dcb_compute_cost(ptr(h), ptr(self.kept_ids), ptr(self.node_g), ptr(self.node_solved), self.weight,

@@ -207,6 +207,10 @@ int dcb_resnet_gemm(const void *d_a_hi, const void *d_a_lo, int64_t lda, const v
 /* F.one_hot of the nnet input (pytorch_models.py:49-52) as fp16 [m][k_padded], column = position*depth + value. */
 int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int32_t depth, int32_t k_padded, void *d_out,
                     void *stream);
+/* Same for the listed nodes of a search's node arena (state of node i at d_arena + i*S): state_to_nnet_input
+ * (cube3.py:77-85) and the one-hot encoding in one pass -- the form the A* loop uses for the children that survived CLOSED. */
+int dcb_onehot_fp16_nodes(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, int32_t depth, int32_t k_padded,
+                          void *d_out, void *stream);
 /* fc_out (pytorch_models.py:85): d_out[m] = sum_{n<n_valid} (x_hi+x_lo)[m][n] * d_w[n] + bias, fp32. */
 int dcb_rowdot(const void *d_x_hi, const void *d_x_lo, const float *d_w, float bias, int64_t m, int32_t n_valid, int32_t ld,
                float *d_out, void *stream);

@@ -122,3 +122,28 @@ def test_tc_network_golden_reference_values(golden_dir):
     x = torch.from_numpy(OracleCube3().nnet_input(g["states"])).cuda()
     got = TcResnet(model, torch.device("cuda"), "fp16x3")(x).cpu().numpy()
     assert np.abs(got - g["ctg"]).max() < 1e-4
+
+
+def test_eval_nodes_equals_gathered_input_path():
+    """dcb_onehot_fp16_nodes (one-hot straight from the node arena) == dcb_gather_nnet_input + dcb_onehot_fp16."""
+    import random
+    from deepcubea_b200 import _lib
+    from deepcubea_b200.nnet.tc_resnet import TcResnet
+    from oracle.oracle_env import OracleCube3
+    lib = _lib.load(); p = _lib.ptr
+    env = OracleCube3()
+    np.random.seed(5); random.seed(5)
+    states, _ = env.generate_states(3000, (0, 20))
+    arena = torch.from_numpy(np.concatenate([states.reshape(-1), np.zeros(64, np.uint8)])).cuda()
+    ids = torch.from_numpy(np.random.permutation(3000)[:1777].astype(np.int32)).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    a = torch.empty((1777, 384), dtype=torch.float16, device="cuda"); b = torch.empty_like(a)
+    _lib.check(lib.dcb_onehot_fp16_nodes(0, p(arena), p(ids), 1777, 6, 384, p(a), st))
+    x = torch.from_numpy(env.nnet_input(states[ids.cpu().numpy()])).cuda()
+    _lib.check(lib.dcb_onehot_fp16(p(x), 1777, 54, 6, 384, p(b), st))
+    assert torch.equal(a, b)
+    ref = torch.nn.functional.one_hot(x.long(), 6).flatten(1).half()
+    assert torch.equal(a[:, :324], ref) and float(a[:, 324:].abs().max()) == 0.0
+    model, _ = _model()
+    tc = TcResnet(model, torch.device("cuda"), "fp16x3")
+    assert torch.equal(tc.eval_nodes(0, arena, ids, 1777), tc(x))
