@@ -156,6 +156,8 @@ def run_ours(args):
             before = eng.nodes_generated
             eng.step(); k -= 1
             nodes += eng.nodes_generated - before
+            if not eng.done and eng.next_slot + 2 * BATCH + 64 > eng.max_slots:
+                eng.done = 3                      # arena nearly full (never with trained weights): move on to the next instance
             if eng.done:
                 if eng.done == 1:
                     solved += 1; lens.append(len(eng.path_to(eng.goal_id)))

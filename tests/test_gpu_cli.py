@@ -111,3 +111,24 @@ def test_cli_solves_reference_test_states(tmp_path, golden_dir, language, precis
     cmp = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "compare_solutions.py"), "--soln1", str(out / "results.pkl"),
                           "--soln2", str(out / "results.pkl")], capture_output=True, text=True, cwd=ROOT)
     assert cmp.returncode == 0 and "100.00% soln2 equal to soln1" in cmp.stdout
+
+
+def test_bellman_backup_matches_oracle():
+    """search_utils.bellman (utils/search_utils.py:16-32): expand + heuristic + min backup on the GPU env."""
+    import random
+    from deepcubea_b200.utils.env_utils import get_environment
+    from deepcubea_b200.utils.search_utils import bellman
+    from oracle import oracle_env as O
+    from oracle.oracle_bwas import misplaced_heuristic
+    for name in ("cube3", "puzzle24"):
+        env, orc = get_environment(name), O.get_oracle_env(name)
+        np.random.seed(12); random.seed(12)
+        ost, _ = orc.generate_states(300, (0, 5))
+        states = env.unpack(ost)
+        h_np = misplaced_heuristic(orc)
+        backup, per_state, exp = bellman(states, lambda sts: h_np(env.pack(sts)).astype(np.float64), env)
+        och, _ = orc.expand(ost)
+        ref = (1.0 + h_np(och.reshape(-1, orc.state_dim)).astype(np.float64)).reshape(300, orc.num_moves)
+        assert np.allclose(np.stack(per_state), ref)
+        assert np.allclose(backup, ref.min(axis=1) * ~orc.is_solved(ost))
+        assert len(exp) == 300 and len(exp[0]) == orc.num_moves
