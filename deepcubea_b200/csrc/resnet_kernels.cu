@@ -182,6 +182,27 @@ struct PairMaps {              // operand pairs, swept in order; the last one is
   CUtensorMap w[kMaxPairs];
 };
 
+// While an epilogue warp waits for its accumulator it has nothing to do: pull the tile's residual input / fp32 partial sums
+// (one row of 256 columns per thread) into L2, so the row-strided reads later hit L2 instead of DRAM.
+__device__ __forceinline__ void prefetch_epilogue_inputs(const EpilogueArgs &ep, int64_t row, int n0, int64_t M, int Np) {
+  if (row >= M) return;
+  if (ep.skip_hi) {
+    const char *h = reinterpret_cast<const char *>(ep.skip_hi + row * Np + n0);
+#pragma unroll
+    for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(h + 128 * q));
+    if (ep.skip_lo) {
+      const char *l = reinterpret_cast<const char *>(ep.skip_lo + row * Np + n0);
+#pragma unroll
+      for (int q = 0; q < 4; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(l + 128 * q));
+    }
+  }
+  if (ep.partial_in) {
+    const char *f = reinterpret_cast<const char *>(ep.partial_in + row * Np + n0);
+#pragma unroll
+    for (int q = 0; q < 8; q++) asm volatile("prefetch.global.L2 [%0];" ::"l"(f + 128 * q));
+  }
+}
+
 // One accumulator tile (this warp's 32 TMEM lanes x 256 columns) -> global memory.  A thread owns one output row; results
 // leave through a per-warp XOR-swizzled shared-memory tile so that eight lanes write one full 128-byte line of a row.
 __device__ __forceinline__ void epilogue_tile(const EpilogueArgs &ep, uint32_t taddr, int64_t row0, int n0, int64_t M, int Np, int lane,
@@ -358,6 +379,7 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
     for (int64_t t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int64_t row0 = (t / n_tiles) * BM + lane_grp * 32;
       const int n0 = (int)((t % n_tiles) * BN);
+      prefetch_epilogue_inputs(ep, row0 + lane, n0, M, Np);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
@@ -562,6 +584,7 @@ resnet_gemm_pair_kernel(const __grid_constant__ PairMaps maps, int n_pairs, Epil
     for (int64_t t = tile_first; t < total_tiles; t += tile_step) {
       const int64_t row0 = (2 * (t / n_tiles) + rank) * BM + lane_grp * 32;
       const int n0 = (int)((t % n_tiles) * BN);
+      prefetch_epilogue_inputs(ep, row0 + lane, n0, M, Np);
       mbar_wait(&tmem_full[buf], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
