@@ -134,6 +134,91 @@ def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], 
             "closed_size": len(closed)}
 
 
+def bwas_python(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], weight: float, batch_size: int,
+                batch_dedup: str = "sequential", keep_trace: bool = False, max_steps: int = 100000,
+                cost_dtype=np.float64) -> Dict:
+    """The reference's PYTHON variant (search_methods/astar.py:232-340 `AStar`, :50-90 `Instance`, :99-209) for one instance:
+      * root evaluated by the heuristic, pushed to OPEN, NOT put in CLOSED (:244-249, 50-62);
+      * every step pops min(batch, |OPEN|) nodes in (cost, push order) order -- heapq FIFO ties (:64-76); solved pops are
+        recorded as goal nodes (:73) and the caller stops after a step that found one (:421); ALL popped nodes are expanded;
+      * cost = weight * g + h * (!solved) (:196, float64 in the reference; `cost_dtype=np.float32` mirrors the GPU engine,
+        identical whenever weight * g is exact, e.g. weight 1.0 / 0.5);
+      * CLOSED keeps a child iff unseen or strictly cheaper (:78-90); nodes generated = sum of children (:168);
+      * answer = goal node with the smallest path cost (:327-333).
+    Node ids as in `bwas` (push order == id order, so FIFO ties == smaller id first).
+    Pinned by tests/golden/astar_python_traces.json (the reference's own AStar run in the build container)."""
+    A, S = env.num_moves, env.state_dim
+    align = slot_align(S, A)
+    ct = cost_dtype
+    states: Dict[int, np.ndarray] = {0: np.asarray(start, dtype=np.uint8).copy()}
+    depth: Dict[int, int] = {0: 0}
+    solved: Dict[int, bool] = {0: bool(env.is_solved(states[0][None])[0])}
+    parent: Dict[int, int] = {}
+    closed: Dict[bytes, List[int]] = {}
+    h0 = np.maximum(np.asarray(heuristic(states[0][None]), dtype=np.float32), np.float32(0.0))[0]
+    open_heap = [(ct(ct(weight) * ct(0)) + ct(h0) * ct(0.0 if solved[0] else 1.0), 0)]
+    next_slot = 1
+    nodes_generated = 0
+    goals: List[int] = []
+    steps = 0
+    trace = []
+    popped_per_step = []
+    while not goals and open_heap and steps < max_steps:
+        num_pop = min(len(open_heap), batch_size)
+        popped = [heapq.heappop(open_heap)[1] for _ in range(num_pop)]
+        goals.extend(p for p in popped if solved[p])
+        popped_per_step.append(num_pop)
+        steps += 1
+        base_slot = -(-next_slot // align) * align
+        par = np.stack([states[p] for p in popped])
+        ch, _ = env.expand(par)
+        flat = ch.reshape(-1, S)
+        sv = env.is_solved(flat)
+        ids = [(base_slot + j) * A + a for j in range(len(popped)) for a in range(A)]
+        dep = [depth[p] + 1 for p in popped for _ in range(A)]
+        next_slot = base_slot + len(popped)
+        nodes_generated += len(ids)
+        keep = [False] * len(ids)
+        if batch_dedup == "sequential":
+            for i in range(len(ids)):
+                key = flat[i].tobytes()
+                e = closed.get(key)
+                if e is None or e[0] > dep[i]:
+                    closed[key] = [dep[i], ids[i]]; keep[i] = True
+        else:
+            best: Dict[bytes, int] = {}
+            for i in range(len(ids)):
+                key = flat[i].tobytes()
+                j = best.get(key)
+                if j is None or (dep[i], ids[i]) < (dep[j], ids[j]):
+                    best[key] = i
+            for key, i in best.items():
+                e = closed.get(key)
+                if e is None or e[0] > dep[i]:
+                    closed[key] = [dep[i], ids[i]]; keep[i] = True
+        kept = [i for i in range(len(ids)) if keep[i]]
+        for i, nid in enumerate(ids):
+            states[nid] = flat[i]; depth[nid] = dep[i]; solved[nid] = bool(sv[i]); parent[nid] = popped[i // A]
+        if kept:
+            h = np.maximum(np.asarray(heuristic(flat[kept]), dtype=np.float32), np.float32(0.0))
+            for k, i in enumerate(kept):
+                cost = ct(ct(weight) * ct(dep[i])) + ct(h[k]) * ct(0.0 if sv[i] else 1.0)
+                heapq.heappush(open_heap, (cost, ids[i]))
+        if keep_trace:
+            trace.append({"popped": list(popped), "kept": [ids[i] for i in kept]})
+    moves = None
+    goal_id = None
+    if goals:
+        goal_id = goals[int(np.argmin([depth[g] for g in goals]))]
+        moves = []
+        nid = goal_id
+        while nid != 0:
+            moves.append(nid % A); nid = parent[nid]
+        moves.reverse()
+    return {"moves": moves, "nodes_generated": nodes_generated, "steps": steps, "goal_id": goal_id, "trace": trace,
+            "popped_per_step": popped_per_step, "open_size": len(open_heap), "closed_size": len(closed)}
+
+
 def misplaced_heuristic(env):
     """An exactly-representable heuristic for bit-exact engine tests: (#positions != goal) / 8 on nnet input."""
     goal_in = env.nnet_input(env.goal[None])[0]

@@ -53,3 +53,29 @@ def test_solved_start_and_empty_solution():
     ref = bwas(env, env.goal, misplaced_heuristic(env), 0.8, 100)
     assert got.moves == [] == ref["moves"]
     assert got.nodes_generated == ref["nodes_generated"]
+
+
+@pytest.mark.parametrize("name,back,batch,weight", [("cube3", (4, 8), 10, 1.0), ("cube3", (5, 9), 100, 0.5), ("cube3", (3, 6), 1, 1.0),
+                                                     ("puzzle15", (10, 24), 7, 0.5), ("puzzle48", (10, 30), 33, 1.0)])
+def test_engine_python_semantics_matches_oracle_trace(name, back, batch, weight):
+    """semantics="python" (the `AStar` class path, astar.py:232-340) trace-exact against oracle.bwas_python (itself pinned to
+    the reference's Python AStar)."""
+    from deepcubea_b200.search.bwas_gpu import BWASGpu
+    from oracle.oracle_bwas import bwas_python
+    env = O.get_oracle_env(name)
+    np.random.seed(17); random.seed(17)
+    states, _ = env.generate_states(5, back)
+    eng = BWASGpu(name, _torch_misplaced(env), weight, batch, max_nodes=1 << 20, semantics="python")
+    for s in states:
+        ref = bwas_python(env, s, misplaced_heuristic(env), weight, batch, batch_dedup="min", keep_trace=True, cost_dtype=np.float32)
+        eng.reset(s)
+        trace = []
+        while not eng.goal_ids and eng.iterations < 3000:
+            trace.append(eng.step(keep_trace=True))
+        assert eng.iterations == ref["steps"]
+        for it, (a, b) in enumerate(zip(trace, ref["trace"])):
+            assert a["popped"] == b["popped"], "step %d popped differ" % it
+            assert a["kept"] == sorted(b["kept"]), "step %d kept differ" % it
+        assert eng.nodes_generated == ref["nodes_generated"]
+        assert eng.goal_id == ref["goal_id"]
+        assert eng.path_to(eng.goal_id) == ref["moves"]
