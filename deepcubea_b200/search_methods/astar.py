@@ -123,7 +123,8 @@ class AStar:
         self.weights: List[float] = weights
         self.step_num: int = 0
         self.timings: Dict[str, float] = {"pop": 0.0, "expand": 0.0, "check": 0.0, "heur": 0.0, "add": 0.0, "itr": 0.0}
-        mn = int(max_nodes or os.environ.get("DCB_MAX_NODES", 1 << 24))
+        # every instance owns a device-resident engine: split a total node budget (default 2^26) over the instances
+        mn = int(max_nodes or os.environ.get("DCB_MAX_NODES", max(1 << 16, (1 << 26) // max(1, len(states)))))
         self.instances: List[Instance] = [Instance(env, s, heuristic_fn, w, mn) for s, w in zip(states, weights)]
         self._batch_size: Optional[int] = None
 
