@@ -44,9 +44,9 @@ int path_device(const uint32_t *slot_parent, uint32_t goal_id, int A, int32_t ma
 using namespace dcb;
 
 namespace {
-const int kStateBytes[DCB_NUM_ENVS] = {54, 16, 25, 36, 49};
-const int kNumMoves[DCB_NUM_ENVS] = {12, 4, 4, 4, 4};
-const int kDim[DCB_NUM_ENVS] = {3, 4, 5, 6, 7};
+const int kStateBytes[DCB_NUM_ENVS] = {54, 16, 25, 36, 49, 49};
+const int kNumMoves[DCB_NUM_ENVS] = {12, 4, 4, 4, 4, 49};
+const int kDim[DCB_NUM_ENVS] = {3, 4, 5, 6, 7, 7};
 inline bool env_ok(int env) { return env >= 0 && env < DCB_NUM_ENVS; }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -84,7 +84,7 @@ int dcb_env_goal_state(int env, uint8_t *h_out) {
   if (!env_ok(env)) return DCB_ERR_BAD_ENV;
   if (!h_out) return DCB_ERR_BAD_ARG;
   const int s = kStateBytes[env];
-  for (int j = 0; j < s; j++) h_out[j] = env == 0 ? (uint8_t)j : (uint8_t)((j + 1) % s);
+  for (int j = 0; j < s; j++) h_out[j] = env == 0 ? (uint8_t)j : (env == DCB_ENV_LIGHTSOUT7 ? (uint8_t)0 : (uint8_t)((j + 1) % s));
   return DCB_OK;
 }
 int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems) {
@@ -97,6 +97,18 @@ int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems) {
     return DCB_OK;
   }
   const int d = kDim[env];
+  if (env == DCB_ENV_LIGHTSOUT7) {              // move_matrix[49][5] of lights_out.py:31-42 / getMoveMat (environments.cpp:133-155)
+    if (capacity_elems < (int64_t)d * d * 5) return DCB_ERR_BAD_ARG;
+    for (int m = 0; m < d * d; m++) {
+      const int x = m / d, y = m % d;
+      h_out[m * 5 + 0] = m;
+      h_out[m * 5 + 1] = x < d - 1 ? m + d : m;
+      h_out[m * 5 + 2] = x > 0 ? m - d : m;
+      h_out[m * 5 + 3] = y < d - 1 ? m + 1 : m;
+      h_out[m * 5 + 4] = y > 0 ? m - 1 : m;
+    }
+    return DCB_OK;
+  }
   if (capacity_elems < (int64_t)d * d * 4) return DCB_ERR_BAD_ARG;
   for (int i = 0; i < d; i++)
     for (int j = 0; j < d; j++) {

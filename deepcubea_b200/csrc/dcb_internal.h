@@ -11,6 +11,8 @@ int dcb_record_cuda(cudaError_t e);
 
 int expand_device(int env, const uint8_t *parents, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved,
                   uint64_t *hash, cudaStream_t st);
+int lightsout_expand_device(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved, uint64_t *hash,
+                            cudaStream_t st);
 int next_state_device(int env, const uint8_t *states, int64_t n, int action, uint8_t *out, cudaStream_t st);
 int is_solved_device(int env, const uint8_t *states, int64_t n, uint8_t *out, cudaStream_t st);
 int hash_states_device(int env, const uint8_t *states, int64_t n, uint64_t *out, cudaStream_t st);

@@ -164,14 +164,21 @@ __global__ void __launch_bounds__(256) state_kernel(const uint8_t *__restrict__ 
       out_hash[p] = state_hash<Sh::W>(w);
     } else {
       uint32_t zm[Sh::W], c[Sh::W];
-      if constexpr (EnvTraits<ENV>::kPuzzle) puzzle_blank_mask<EnvTraits<ENV>::DIM, Sh::W>(w, zm);
-      else {
+      if constexpr (ENV == 5) {                     // Lights Out: XOR with the press mask (lights_out.py:156-166)
+        uint32_t mk[Sh::W];
+        lo_words_from_bits<Sh::S, Sh::W>(lo_press_mask<EnvTraits<ENV>::DIM>(action), mk);
 #pragma unroll
-        for (int i = 0; i < Sh::W; i++) zm[i] = 0;
+        for (int i = 0; i < Sh::W; i++) { zm[i] = 0; c[i] = w[i] ^ mk[i]; }
+      } else {
+        if constexpr (EnvTraits<ENV>::kPuzzle) puzzle_blank_mask<EnvTraits<ENV>::DIM, Sh::W>(w, zm);
+        else {
+#pragma unroll
+          for (int i = 0; i < Sh::W; i++) zm[i] = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < Sh::W; i++) c[i] = w[i];
+        ApplyAction<ENV, 0>::run(action, w, zm, c);
       }
-#pragma unroll
-      for (int i = 0; i < Sh::W; i++) c[i] = w[i];
-      ApplyAction<ENV, 0>::run(action, w, zm, c);
       uint8_t *o = out_states + off;
       if constexpr (Sh::S % 4 == 0) {
 #pragma unroll
@@ -287,6 +294,7 @@ static int dispatch_expand(int env, const uint8_t *src, const uint32_t *ids, int
     case 2: return launch_expand<2, INDEXED>(src, ids, n, children, solved, hash, st);
     case 3: return launch_expand<3, INDEXED>(src, ids, n, children, solved, hash, st);
     case 4: return launch_expand<4, INDEXED>(src, ids, n, children, solved, hash, st);
+    case 5: return lightsout_expand_device(src, ids, n, children, solved, hash, st);
   }
   return DCB_ERR_BAD_ENV;
 }
@@ -310,6 +318,7 @@ static int dispatch_state(int env, const uint8_t *states, int64_t n, int action,
     case 2: state_kernel<2, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     case 3: state_kernel<3, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     case 4: state_kernel<4, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 5: state_kernel<5, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     default: return DCB_ERR_BAD_ENV;
   }
   return dcb_check_launch();

@@ -17,6 +17,7 @@ template <> struct EnvTraits<1> { static constexpr int S = 16, A = 4, DIM = 4; s
 template <> struct EnvTraits<2> { static constexpr int S = 25, A = 4, DIM = 5; static constexpr bool kPuzzle = true; };
 template <> struct EnvTraits<3> { static constexpr int S = 36, A = 4, DIM = 6; static constexpr bool kPuzzle = true; };
 template <> struct EnvTraits<4> { static constexpr int S = 49, A = 4, DIM = 7; static constexpr bool kPuzzle = true; };
+template <> struct EnvTraits<5> { static constexpr int S = 49, A = 49, DIM = 7; static constexpr bool kPuzzle = false; };   // Lights Out 7x7
 
 DCB_HOSTDEV constexpr int hash_words(int s) { return 2 * ((s + 7) / 8); }
 DCB_HOSTDEV constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) ? 2 : 1); }
@@ -53,8 +54,8 @@ template <int W> DCB_DEV uint64_t state_hash(const uint32_t (&w)[W]) {
 // Goal states
 // ---------------------------------------------------------------------------------------------------
 template <int ENV> DCB_HOSTDEV constexpr uint8_t goal_byte(int j) {
-  // cube3: sticker identity (cube3.py:37, :71-75).  n-puzzle: [1..n*n-1, 0] (n_puzzle.py:41).
-  return ENV == 0 ? (uint8_t)j : (uint8_t)((j + 1) % EnvTraits<ENV>::S);
+  // cube3: sticker identity (cube3.py:37, :71-75).  n-puzzle: [1..n*n-1, 0] (n_puzzle.py:41).  Lights Out: all off.
+  return ENV == 0 ? (uint8_t)j : (ENV == 5 ? (uint8_t)0 : (uint8_t)((j + 1) % EnvTraits<ENV>::S));
 }
 template <int ENV> DCB_HOSTDEV constexpr uint32_t goal_word(int w) {
   constexpr int S = EnvTraits<ENV>::S;
@@ -150,6 +151,35 @@ template <int DIM, int MOVE, int W> DCB_DEV void puzzle_child(const uint32_t (&p
 template <int DIM, int W> DCB_DEV void puzzle_blank_mask(const uint32_t (&p)[W], uint32_t (&zm)[W]) {
 #pragma unroll
   for (int w = 0; w < W; w++) zm[w] = __vcmpeq4(p[w], 0u) & valid_mask<DIM * DIM>(w);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Lights Out (environments/lights_out.py:26-166, cpp/environments.cpp:133-208): a state is DIM*DIM cells of 0/1, i.e. a
+// 49-bit word for the 7x7 board; pressing cell m toggles m and its in-board neighbours m+-DIM (x axis) and m+-1 (y axis).
+// All arithmetic happens on the bit form; bytes <-> bits conversions are multiply tricks on 4-byte words.
+// ---------------------------------------------------------------------------------------------------
+template <int DIM> DCB_HOSTDEV uint64_t lo_press_mask(int m) {
+  const int x = m / DIM, y = m % DIM;                       // lights_out.py:34-42
+  uint64_t k = 1ull << m;
+  if (x < DIM - 1) k |= 1ull << (m + DIM);
+  if (x > 0) k |= 1ull << (m - DIM);
+  if (y < DIM - 1) k |= 1ull << (m + 1);
+  if (y > 0) k |= 1ull << (m - 1);
+  return k;
+}
+// 4 cells (one per byte, values 0/1) -> 4 bits
+DCB_HOSTDEV uint32_t lo_pack4(uint32_t w) { return (((w & 0x01010101u) * 0x01020408u) >> 24) & 0xFu; }
+// 4 bits -> 4 cells (one per byte)
+DCB_HOSTDEV uint32_t lo_spread4(uint32_t nib) { return ((nib & 0xFu) * 0x00204081u) & 0x01010101u; }
+template <int W> DCB_DEV uint64_t lo_bits_from_words(const uint32_t (&w)[W]) {
+  uint64_t b = 0;
+#pragma unroll
+  for (int k = 0; k < W; k++) b |= (uint64_t)lo_pack4(w[k]) << (4 * k);
+  return b;
+}
+template <int S, int W> DCB_DEV void lo_words_from_bits(uint64_t bits, uint32_t (&w)[W]) {
+#pragma unroll
+  for (int k = 0; k < W; k++) w[k] = lo_spread4((uint32_t)(bits >> (4 * k))) & valid_mask<S>(k);
 }
 
 // ---------------------------------------------------------------------------------------------------

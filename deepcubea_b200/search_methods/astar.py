@@ -75,7 +75,10 @@ def _device_heuristic(heuristic_fn: Callable, env: Environment) -> Callable[[tor
 
 
 def _env_name(env: Environment) -> str:
-    return "cube3" if type(env).__name__ == "Cube3" else "puzzle%d" % (env.dim * env.dim - 1)
+    kind = type(env).__name__
+    if kind == "Cube3":
+        return "cube3"
+    return "lightsout%d" % env.dim if kind == "LightsOut" else "puzzle%d" % (env.dim * env.dim - 1)
 
 
 class Instance:

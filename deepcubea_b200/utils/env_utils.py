@@ -14,6 +14,9 @@ def get_environment(env_name: str) -> Environment:
     if m is not None:
         from ..environments.n_puzzle import NPuzzle
         return NPuzzle(int(math.sqrt(int(m.group(1)) + 1)))
-    if "lightsout" in name or name == "sokoban":
-        raise ValueError("%s is outside the B200 hot path (cube3 and puzzle15/24/35/48 only)" % env_name)
+    if "lightsout" in name:
+        from ..environments.lights_out import LightsOut
+        return LightsOut(int(re.search(r"lightsout(\d+)", name).group(1)))
+    if name == "sokoban":
+        raise ValueError("%s is outside the B200 hot path (cube3, puzzle15/24/35/48, lightsout7)" % env_name)
     raise ValueError("No known environment %s" % env_name)

@@ -52,6 +52,25 @@ void oracle_puzzle_expand(const uint8_t *parents, int64_t n, int dim, const int3
   }
 }
 
+/* cpp/environments.cpp:171-196 (LightsOut::getNextState(s): newState[moveMat[a][i]] = (state[...] + 1) % 2 from the ORIGINAL
+ * state) + :198-206 (isSolved: all zero). */
+void oracle_lightsout_expand(const uint8_t *parents, int64_t n, int dim, const int32_t *move_mat /*[dim*dim][5]*/,
+                             uint8_t *children /*[n][dim*dim][dim*dim]*/, uint8_t *solved /*[n][dim*dim]*/) {
+  const int s = dim * dim;
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < n; p++) {
+    const uint8_t *cur = parents + p * s;
+    for (int a = 0; a < s; a++) {
+      uint8_t *nxt = children + (p * s + a) * s;
+      memcpy(nxt, cur, (size_t)s);
+      for (int i = 0; i < 5; i++) nxt[move_mat[a * 5 + i]] = (uint8_t)((cur[move_mat[a * 5 + i]] + 1) % 2);
+      uint8_t ok = 1;
+      for (int i = 0; i < s; i++) ok &= (uint8_t)(nxt[i] == 0);
+      solved[p * s + a] = ok;
+    }
+  }
+}
+
 void oracle_hash64(const uint8_t *states, int64_t n, int state_dim, const uint32_t *keys /*[16]*/,
                    uint64_t seed, uint64_t *out) {
   const int w = 2 * ((state_dim + 7) / 8);

@@ -141,11 +141,78 @@ class OracleNPuzzle:
         return st, scr
 
 
+class OracleLightsOut:
+    """environments/lights_out.py:26-166 and cpp/environments.cpp:133-208."""
+
+    def __init__(self, dim: int = 7):
+        self.dim = dim
+        self.state_dim = dim * dim
+        self.num_moves = dim * dim
+        self.name = "lightsout%d" % dim
+        self.move_matrix = self.build_move_matrix(dim)                   # lights_out.py:31-42
+        self.goal = np.zeros(self.state_dim, dtype=np.uint8)             # lights_out.py:56-64
+        self.rev_action = list(range(self.num_moves))                    # a press undoes itself (lights_out.py:53-54)
+
+    @staticmethod
+    def build_move_matrix(dim: int) -> np.ndarray:
+        """[move, move+dim, move-dim, move+1, move-1] with an out-of-board neighbour replaced by `move` itself."""
+        mm = np.zeros((dim * dim, 5), dtype=np.int64)
+        for move in range(dim * dim):
+            x, y = move // dim, move % dim
+            mm[move] = [move, move + dim if x < dim - 1 else move, move - dim if x > 0 else move,
+                        move + 1 if y < dim - 1 else move, move - 1 if y > 0 else move]
+        return mm
+
+    def move_many(self, states: np.ndarray, actions) -> np.ndarray:
+        """lights_out.py:156-166 `_move_np`: every listed cell becomes (old + 1) % 2 of the ORIGINAL state, so a cell listed
+        twice (board edge) still toggles once -- same as LightsOut::getNextState (environments.cpp:171-183)."""
+        nxt = states.copy()
+        rows = np.arange(states.shape[0])[:, None]
+        mm = self.move_matrix[np.asarray(actions)]
+        nxt[rows, mm] = (states[rows, mm] + 1) % 2
+        return nxt
+
+    def move(self, states: np.ndarray, action: int) -> np.ndarray:
+        return self.move_many(states, [action] * states.shape[0])
+
+    def prev(self, states: np.ndarray, action: int) -> np.ndarray:
+        return self.move(states, action)
+
+    def is_solved(self, states: np.ndarray) -> np.ndarray:
+        return np.all(states == 0, axis=1)                               # lights_out.py:66-69
+
+    def nnet_input(self, states: np.ndarray) -> np.ndarray:
+        return states.astype(np.uint8)                                   # lights_out.py:71-76
+
+    def expand(self, states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        ch = np.stack([self.move(states, a) for a in range(self.num_moves)], axis=1)
+        return ch, np.ones((states.shape[0], self.num_moves), dtype=np.float64)
+
+    def generate_states(self, n: int, back: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
+        """lights_out.py:86-119: one pre-drawn move table, states advance in lock step (same RNG call sequence)."""
+        scrambs = list(range(back[0], back[1] + 1))
+        st = np.zeros((n, self.state_dim), dtype=np.uint8)
+        scr = np.random.choice(scrambs, n)
+        nb = np.zeros(n)
+        moves = np.random.choice(self.num_moves, size=(n, max(scrambs)))
+        k = 0
+        lt = nb < scr
+        while np.any(lt):
+            idxs = np.where(lt)[0]
+            st[idxs] = self.move_many(st[idxs], list(moves[idxs, k]))
+            nb[idxs] = nb[idxs] + 1
+            lt[idxs] = nb[idxs] < scr[idxs]
+            k += 1
+        return st, scr
+
+
 def get_oracle_env(name: str):
-    """utils/env_utils.py:6-28 (cube3 and puzzle(\\d+) only)."""
+    """utils/env_utils.py:6-28 (cube3, puzzle(\\d+), lightsout(\\d+))."""
     name = name.lower()
     if name == "cube3":
         return OracleCube3()
+    if name.startswith("lightsout"):
+        return OracleLightsOut(int(name[9:]))
     if name.startswith("puzzle"):
         return OracleNPuzzle(int(round((int(name[6:]) + 1) ** 0.5)))
     raise ValueError("No known environment %s" % name)

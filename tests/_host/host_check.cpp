@@ -48,6 +48,25 @@ template <int ENV> void next_env(const uint8_t *states, int64_t n, int action, u
 }
 }  // namespace
 
+// Lights Out 7x7: the bit-form math of csrc/lightsout_kernels.cu (bytes -> bits, press masks, bits -> bytes, hash, solved)
+extern "C" int hc_lightsout_expand(const uint8_t *parents, int64_t n, uint8_t *children, uint8_t *solved, uint64_t *hash) {
+  constexpr int S = 49, A = 49, W = 14;
+  for (int64_t p = 0; p < n; p++) {
+    uint32_t w[W];
+    load_words<5>(parents, p * S, w);
+    const uint64_t pb = lo_bits_from_words<W>(w);
+    for (int m = 0; m < A; m++) {
+      const uint64_t b = pb ^ lo_press_mask<7>(m);
+      uint32_t c[W];
+      lo_words_from_bits<S, W>(b, c);
+      std::memcpy(children + (p * A + m) * S, c, S);
+      hash[p * A + m] = state_hash<W>(c);
+      solved[p * A + m] = b == 0;
+    }
+  }
+  return 0;
+}
+
 // `parents` must be readable for 4 bytes past the end (callers pad).
 extern "C" int hc_expand(int env, const uint8_t *parents, int64_t n, uint8_t *children, uint8_t *solved, uint64_t *hash) {
   switch (env) {

@@ -10,7 +10,7 @@ from oracle import oracle_env as O
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-ENVS = ["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48"]
+ENVS = ["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7"]
 
 
 def _states(name, n, seed, back):
@@ -59,7 +59,17 @@ def test_puzzle_config1_golden(golden_dir, name):
     assert np.array_equal(np.packbits(sv.cpu().numpy().astype(bool)), g["solved"])
 
 
-@pytest.mark.parametrize("name", ["cube3", "puzzle15", "puzzle48"])
+def test_lightsout_config1_golden(golden_dir):
+    from deepcubea_b200 import ops
+    g = np.load(golden_dir + "/lightsout7_cfg1.npz")
+    ch, sv, _ = ops.expand(5, torch.from_numpy(g["parents"]).cuda())
+    ch = ch.cpu().numpy()
+    assert hashlib.sha256(ch.tobytes()).hexdigest() == str(g["children_sha256"])
+    assert np.array_equal(ch[:64], g["children_head"])
+    assert np.array_equal(np.packbits(sv.cpu().numpy().astype(bool)), g["solved"])
+
+
+@pytest.mark.parametrize("name", ["cube3", "puzzle15", "puzzle48", "lightsout7"])
 def test_golden_triples(golden_dir, name):
     """Every (s, a, s') of the reference's shipped BWAS results replays bit-exactly through next_state."""
     from deepcubea_b200 import ops, _lib
@@ -86,7 +96,7 @@ def test_single_state_ops(name):
     for a in range(env.num_moves):
         assert np.array_equal(ops.next_state(eid, d, a).cpu().numpy(), env.move(st, a))
         back = ops.next_state(eid, ops.next_state(eid, d, a), env.rev_action[a]).cpu().numpy()
-        if name == "cube3":
+        if name in ("cube3", "lightsout7"):
             assert np.array_equal(back, st)       # move then inverse = identity
     assert np.array_equal(ops.is_solved(eid, d).cpu().numpy().astype(bool), env.is_solved(st))
     assert np.array_equal(ops.hash_states(eid, d).cpu().numpy().view(np.uint64), O.state_hash64(st))

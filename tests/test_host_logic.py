@@ -54,6 +54,21 @@ def test_device_math_on_host_matches_oracle(hostcheck_lib, envid, name):
         assert np.array_equal(out, env.move(st, a))
 
 
+def test_lightsout_device_math_on_host_matches_oracle(hostcheck_lib):
+    env = O.OracleLightsOut(7)
+    np.random.seed(9); random.seed(9)
+    st, _ = env.generate_states(600, (0, 6))
+    n = len(st)
+    buf = np.zeros(n * 49 + 8, np.uint8); buf[:n * 49] = st.reshape(-1)
+    ch = np.zeros((n, 49, 49), np.uint8); sv = np.zeros((n, 49), np.uint8); hs = np.zeros((n, 49), np.uint64)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    assert hostcheck_lib.hc_lightsout_expand(p(buf), ctypes.c_int64(n), p(ch), p(sv), p(hs)) == 0
+    och, _ = env.expand(st)
+    assert np.array_equal(ch, och)
+    assert np.array_equal(sv.astype(bool).reshape(-1), env.is_solved(och.reshape(-1, 49))) and sv.sum() > 0
+    assert np.array_equal(hs.reshape(-1), O.state_hash64(och.reshape(-1, 49)))
+
+
 def test_c_abi_exports_every_declared_symbol():
     """The library loads and exports exactly what include/dcb.h declares (no compute without a GPU)."""
     from deepcubea_b200 import _lib
@@ -64,9 +79,9 @@ def test_c_abi_exports_every_declared_symbol():
         assert hasattr(lib, name), name
     assert declared == _lib.exported_symbols()
     assert lib.dcb_abi_version() == 1
-    assert [lib.dcb_env_state_bytes(e) for e in range(5)] == [54, 16, 25, 36, 49]
-    assert [lib.dcb_env_num_moves(e) for e in range(5)] == [12, 4, 4, 4, 4]
-    assert [lib.dcb_env_slot_align(e) for e in range(5)] == [2, 1, 4, 1, 4]
+    assert [lib.dcb_env_state_bytes(e) for e in range(6)] == [54, 16, 25, 36, 49, 49]
+    assert [lib.dcb_env_num_moves(e) for e in range(6)] == [12, 4, 4, 4, 4, 49]
+    assert [lib.dcb_env_slot_align(e) for e in range(6)] == [2, 1, 4, 1, 4, 16]
     assert lib.dcb_env_state_bytes(9) == -1 and lib.dcb_error_string(-1) == b"unknown environment id"
     assert lib.dcb_expand(9, None, 0, None, None, None, None) == -1            # argument validation happens before any launch
     assert lib.dcb_expand(0, None, 5, None, None, None, None) == -2
@@ -88,6 +103,12 @@ def test_abi_tables_match_reference(golden_dir):
         goal = np.zeros(dim * dim, np.uint8)
         assert lib.dcb_env_goal_state(e, _lib.ptr(goal)) == 0
         assert np.array_equal(goal, np.array(pz[str(dim)]["goal"]))
+    lo = json.load(open(golden_dir + "/lightsout_tables.json"))
+    buf = np.zeros(49 * 5, np.int32)
+    assert lib.dcb_env_move_table(5, _lib.ptr(buf), buf.size) == 0
+    assert np.array_equal(buf.reshape(49, 5), np.array(lo["move_matrix"]))
+    goal = np.ones(49, np.uint8)
+    assert lib.dcb_env_goal_state(5, _lib.ptr(goal)) == 0 and goal.sum() == 0
 
 
 def test_product_fails_loudly_without_gpu():
@@ -118,7 +139,7 @@ def test_product_never_imports_oracle():
 def test_registry_and_plugin_api_surface():
     from deepcubea_b200.environments.environment_abstract import Environment
     from deepcubea_b200.utils.env_utils import get_environment
-    for name, S, A in (("cube3", 54, 12), ("puzzle15", 16, 4), ("PUZZLE24", 25, 4), ("puzzle35", 36, 4), ("puzzle48", 49, 4)):
+    for name, S, A in (("cube3", 54, 12), ("puzzle15", 16, 4), ("PUZZLE24", 25, 4), ("puzzle35", 36, 4), ("puzzle48", 49, 4), ("lightsout7", 49, 49)):
         env = get_environment(name)
         assert isinstance(env, Environment) and env.get_num_moves() == A and env.state_dim == S
         for m in ("next_state", "prev_state", "generate_goal_states", "is_solved", "state_to_nnet_input", "get_nnet_model",
@@ -127,11 +148,12 @@ def test_registry_and_plugin_api_surface():
         goals = env.generate_goal_states(3)
         assert len({hash(g) for g in goals}) == 1 and goals[0] == goals[1]
         assert env.generate_goal_states(2, np_format=True).shape == (2, S)
-    for bad in ("lightsout7", "sokoban", "cube4"):
+    for bad in ("lightsout5", "sokoban", "cube4"):
         with pytest.raises(ValueError):
             get_environment(bad)
     env = get_environment("puzzle15")
     assert np.array_equal(env.swap_zero_idxs, O.OracleNPuzzle(4).swap)
+    assert np.array_equal(get_environment("lightsout7").move_matrix, O.OracleLightsOut(7).move_matrix)
     model = get_environment("cube3").get_nnet_model()
     assert sum(p.numel() for p in model.parameters()) == 14_688_001 or sum(p.numel() for p in model.parameters()) > 14_600_000
 

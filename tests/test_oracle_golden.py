@@ -121,3 +121,32 @@ def test_hash_is_injective_on_fixture_states(golden_dir):
     h = O.state_hash64(flat)
     assert (h != 0).all()
     assert len(np.unique(h)) == len(np.unique(flat, axis=0))
+
+
+def test_lightsout_oracle_reproduces_reference(golden_dir, oracle_clib):
+    """Lights Out 7x7: tables, seeded scrambles, all 49 children, solved flags, the reference's shipped
+    (s, a, s') triples, and the C restatement."""
+    env = O.OracleLightsOut(7)
+    t = json.load(open(golden_dir + "/lightsout_tables.json"))
+    assert np.array_equal(env.move_matrix, np.array(t["move_matrix"]))
+    g = np.load(golden_dir + "/lightsout7_cfg1.npz")
+    np.random.seed(4); random.seed(4)
+    st, depths = env.generate_states(2000, (0, 50))
+    assert np.array_equal(st, g["parents"]) and np.array_equal(depths, g["depths"])
+    ch, _ = env.expand(st)
+    assert _sha(ch) == str(g["children_sha256"]) and np.array_equal(ch[:64], g["children_head"])
+    solved = env.is_solved(ch.reshape(-1, 49)).reshape(2000, 49)
+    assert np.array_equal(np.packbits(solved), g["solved"]) and solved.sum() == int(g["n_solved"])
+    pg = np.load(golden_dir + "/paths_lightsout7.npz")
+    states, moves, offs = pg["states"], pg["moves"], pg["offsets"]
+    is_last = np.zeros(len(states), bool); is_last[offs[1:] - 1] = True
+    src, dst = states[~is_last], states[np.roll(~is_last, 1)]
+    assert len(src) == len(moves) == 12130
+    assert np.array_equal(env.move_many(src, moves), dst)
+    assert np.array_equal(env.is_solved(states), is_last)
+    n = 500
+    c2 = np.empty((n, 49, 49), np.uint8); s2 = np.empty((n, 49), np.uint8)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    mm = np.ascontiguousarray(env.move_matrix, dtype=np.int32)
+    oracle_clib.oracle_lightsout_expand(p(st[:n]), ctypes.c_int64(n), 7, p(mm), p(c2), p(s2))
+    assert np.array_equal(c2, ch[:n]) and np.array_equal(s2.astype(bool), solved[:n])

@@ -1,7 +1,7 @@
 """Solution quality on the reference's own test sets, against the reference's shipped results and the optimal lengths.
     python tools/validate_quality.py <env> [n_states] [precision]  -> prints a table, writes gpurun_out/quality_r01_<env>_<prec>.txt
 Configs = the reference's published runs (train.sh:9 cube3: weight 0.6, batch 10000; train.sh:21 puzzle15: 0.8 / 20000;
-train.sh:57 puzzle48: 0.6 / 20000).  Needs assets/saved_models/<env>/current/model_state_dict.pt (tools/fetch_assets.py <env>)."""
+train.sh:57 puzzle48: 0.6 / 20000; train.sh:68 lightsout7: 0.2 / 1000).  Needs assets/saved_models/<env>/current/model_state_dict.pt (tools/fetch_assets.py <env>)."""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -15,7 +15,7 @@ from deepcubea_b200.utils.nnet_utils import load_nnet
 name = sys.argv[1] if len(sys.argv) > 1 else "cube3"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 prec = sys.argv[3] if len(sys.argv) > 3 else "fp16x3"
-weight, batch = {"cube3": (0.6, 10000), "puzzle15": (0.8, 20000), "puzzle48": (0.6, 20000)}[name]
+weight, batch = {"cube3": (0.6, 10000), "puzzle15": (0.8, 20000), "puzzle48": (0.6, 20000), "lightsout7": (0.2, 1000)}[name]
 env = get_environment(name); eid = _lib.ENV_IDS[name]
 model = load_nnet(os.path.join(ROOT, "assets/saved_models/%s/current/model_state_dict.pt" % name), env.get_nnet_model(), device=torch.device("cpu"))
 dev = torch.device("cuda")
