@@ -13,7 +13,7 @@
 //   2. entries of that boundary bucket (typically a handful) are collected and a single block finishes
 //      the select on their remaining 40 bits -> exact threshold T;
 //   3. one partition pass removes everything <= T, back-filling the holes from the array tail;
-//   4. the popped list is rank-sorted into cost order (the reference's pop order, so child node ids are
+//   4. the popped list is sorted (bucketed rank sort) into cost order (the reference's pop order, so child node ids are
 //      deterministic) and the goal / termination rule of :190-208 is applied on the device; entries behind
 //      the first solved pop go back to OPEN, exactly like the reference's `break`.
 // HBM traffic per pop: 4 passes x 4 B per open entry; per push: 8 B per entry.
@@ -69,8 +69,19 @@ open_push_kernel(OpenState *s, uint32_t *key, uint32_t *id, uint32_t capacity, c
 }
 
 // ---- pop ------------------------------------------------------------------------------------------
-__global__ void open_pop_begin_kernel(OpenState *s, uint32_t *hist, int32_t batch) {
+constexpr int kSortBins = 4096;
+struct SortScratch {                     // lives in the pop scratch buffer
+  unsigned long long min64;            // smallest / largest popped composite (set by the partition pass)
+  unsigned long long max64;
+  uint32_t counts[kSortBins + 1];      // bucket sizes, then (after the scan) bucket start offsets
+  uint32_t cursor[kSortBins];
+};
+
+__global__ void open_pop_begin_kernel(OpenState *s, uint32_t *hist, int32_t batch, SortScratch *ss) {
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) hist[i] = 0;
+  for (int i = threadIdx.x; i <= kSortBins; i += blockDim.x) ss->counts[i] = 0;
+  for (int i = threadIdx.x; i < kSortBins; i += blockDim.x) ss->cursor[i] = 0;
+  if (threadIdx.x == 0) { ss->min64 = ~0ull; ss->max64 = 0ull; }
   if (threadIdx.x == 0) {
     const uint32_t n = s->size;
     const uint32_t b = n < (uint32_t)batch ? n : (uint32_t)batch;
@@ -193,7 +204,7 @@ __global__ void __launch_bounds__(1024) open_select_finish_kernel(OpenState *s, 
 // Partition: pop everything <= threshold; remember holes in the kept prefix and survivors in the tail.
 __global__ void __launch_bounds__(512)
 open_partition_kernel(OpenState *s, const uint32_t *__restrict__ key, const uint32_t *__restrict__ id, int32_t batch,
-                      unsigned long long *popped, uint32_t *holes, uint32_t *surv) {
+                      unsigned long long *popped, uint32_t *holes, uint32_t *surv, SortScratch *ss) {
   const uint32_t n = s->n_at_pop;
   const uint32_t b = n < (uint32_t)batch ? n : (uint32_t)batch;
   const uint32_t new_size = n - b;
@@ -212,7 +223,12 @@ open_partition_kernel(OpenState *s, const uint32_t *__restrict__ key, const uint
       sv = !pop && i >= new_size;
     }
     const uint32_t pp = warp_agg_inc(&s->n_popped, pop);
-    if (pop) popped[pp] = ((unsigned long long)k << 32) | d;
+    if (pop) {
+      const unsigned long long v = ((unsigned long long)k << 32) | d;
+      popped[pp] = v;
+      atomicMin(&ss->min64, v);
+      atomicMax(&ss->max64, v);
+    }
     const uint32_t hp = warp_agg_inc(&s->n_holes, hole);
     if (hole) holes[hp] = i;
     const uint32_t sp = warp_agg_inc(&s->n_surv, sv);
@@ -228,23 +244,60 @@ __global__ void __launch_bounds__(256) open_fill_holes_kernel(const OpenState *s
   }
 }
 
-// Rank-sort the popped composites (all distinct) into cost order.
-__global__ void __launch_bounds__(256)
-open_sort_popped_kernel(const OpenState *s, const unsigned long long *__restrict__ popped, unsigned long long *sorted) {
-  __shared__ unsigned long long tile[1024];
-  const uint32_t b = s->n_popped;
-  if (blockIdx.x * blockDim.x >= b) return;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned long long mine = i < b ? popped[i] : ~0ull;
-  uint32_t rank = 0;
-  for (uint32_t j0 = 0; j0 < b; j0 += 1024) {
+// Sorting the popped composites (all distinct) into cost order = the reference's pop order.  Bucket by a monotone map of
+// the value onto kSortBins equal slices of [min, threshold], counting-sort into bucket order, then rank only within a
+// bucket (a handful of elements): O(b) instead of the O(b^2) plain rank sort (175 us at b = 20000).
+__device__ __forceinline__ uint32_t sort_bucket(unsigned long long v, unsigned long long lo, double scale) {
+  const double x = (double)(v - lo) * scale;                  // monotone in v
+  const uint32_t b = (uint32_t)x;
+  return b < (uint32_t)kSortBins ? b : (uint32_t)(kSortBins - 1);
+}
+__device__ __forceinline__ double sort_scale(const OpenState *, const SortScratch *ss) {
+  const unsigned long long hi = ss->max64, lo = ss->min64;
+  return (hi >= lo) ? (double)kSortBins / ((double)(hi - lo) + 1.0) : 0.0;
+}
+__global__ void __launch_bounds__(256) open_sort_count_kernel(const OpenState *s, const unsigned long long *__restrict__ popped, SortScratch *ss) {
+  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  atomicAdd(&ss->counts[sort_bucket(popped[i], ss->min64, sort_scale(s, ss))], 1u);
+}
+__global__ void __launch_bounds__(1024) open_sort_scan_kernel(SortScratch *ss) {      // exclusive scan of kSortBins counts
+  __shared__ uint32_t part[1024];
+  const int t = threadIdx.x;
+  uint32_t c[4], sum = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) { c[q] = ss->counts[4 * t + q]; sum += c[q]; }
+  part[t] = sum;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = (t >= off) ? part[t - off] : 0;
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < 1024; j += blockDim.x) tile[j] = (j0 + j < b) ? popped[j0 + j] : ~0ull;
+    part[t] += v;
     __syncthreads();
-    const uint32_t lim = (b - j0) < 1024u ? (b - j0) : 1024u;
-    for (uint32_t j = 0; j < lim; j++) rank += tile[j] < mine;
   }
-  if (i < b) sorted[rank] = mine;
+  uint32_t run = part[t] - sum;
+#pragma unroll
+  for (int q = 0; q < 4; q++) { ss->counts[4 * t + q] = run; run += c[q]; }
+  if (t == 1023) ss->counts[kSortBins] = run;
+}
+__global__ void __launch_bounds__(256)
+open_sort_scatter_kernel(const OpenState *s, const unsigned long long *__restrict__ popped, SortScratch *ss, unsigned long long *tmp) {
+  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const unsigned long long v = popped[i];
+  const uint32_t k = sort_bucket(v, ss->min64, sort_scale(s, ss));
+  tmp[ss->counts[k] + atomicAdd(&ss->cursor[k], 1u)] = v;
+}
+__global__ void __launch_bounds__(256)
+open_sort_rank_kernel(const OpenState *s, const SortScratch *ss, const unsigned long long *__restrict__ tmp, unsigned long long *sorted) {
+  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= b) return;
+  const unsigned long long v = tmp[i];
+  const uint32_t k = sort_bucket(v, ss->min64, sort_scale(s, ss));
+  const uint32_t lo = ss->counts[k], hi = ss->counts[k + 1];
+  uint32_t rank = lo;
+  for (uint32_t j = lo; j < hi; j++) rank += tmp[j] < v;
+  sorted[rank] = v;
 }
 
 // Single block: goal bookkeeping + termination (parallel_weighted_astar.cpp:186-208) and un-popping the
@@ -308,30 +361,38 @@ int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity,
   return dcb_check_launch();
 }
 
-// scratch layout (bytes): hist 2*4096*4 | cand 8*cap | popped 8*batch | sorted 8*batch | holes 4*batch | surv 4*batch
-int64_t open_scratch_bytes(int64_t capacity, int64_t batch) { return 2 * kBins * 4 + 8 * capacity + 24 * batch + 256; }
+// scratch layout (bytes): hist 2*4096*4 | sort scratch | cand 8*cap | popped 8*batch | sorted 8*batch | tmp 8*batch | holes 4*batch | surv 4*batch
+int64_t open_scratch_bytes(int64_t capacity, int64_t batch) {
+  return 2 * kBins * 4 + (int64_t)((sizeof(SortScratch) + 15) / 16 * 16) + 8 * capacity + 32 * batch + 256;
+}
 
 int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, int32_t batch, int stop_at_goal,
                     const uint8_t *node_solved, uint32_t *popped_ids, void *scratch, cudaStream_t st) {
   OpenState *s = reinterpret_cast<OpenState *>(state);
   uint8_t *p = reinterpret_cast<uint8_t *>(scratch);
   uint32_t *hist = reinterpret_cast<uint32_t *>(p); p += 2 * kBins * 4;
+  SortScratch *ss = reinterpret_cast<SortScratch *>(p); p += (sizeof(SortScratch) + 15) / 16 * 16;
   unsigned long long *cand = reinterpret_cast<unsigned long long *>(p); p += 8 * capacity;
   unsigned long long *popped = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
   unsigned long long *sorted = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
+  unsigned long long *tmp = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
   uint32_t *holes = reinterpret_cast<uint32_t *>(p); p += 4 * (int64_t)batch;
   uint32_t *surv = reinterpret_cast<uint32_t *>(p);
   const int full_blocks = 148 * 4;   // grid-stride passes over the whole array
-  open_pop_begin_kernel<<<1, 1024, 0, st>>>(s, hist, batch);
+  open_pop_begin_kernel<<<1, 1024, 0, st>>>(s, hist, batch, ss);
   open_hist_kernel<0><<<full_blocks, 512, 0, st>>>(s, key, hist);
   open_scan_kernel<0><<<1, 1024, 0, st>>>(s, hist);
   open_hist_kernel<1><<<full_blocks, 512, 0, st>>>(s, key, hist);
   open_scan_kernel<1><<<1, 1024, 0, st>>>(s, hist);
   open_collect_kernel<<<full_blocks, 512, 0, st>>>(s, key, id, cand);
   open_select_finish_kernel<<<1, 1024, 0, st>>>(s, cand);
-  open_partition_kernel<<<full_blocks, 512, 0, st>>>(s, key, id, batch, popped, holes, surv);
+  open_partition_kernel<<<full_blocks, 512, 0, st>>>(s, key, id, batch, popped, holes, surv, ss);
   open_fill_holes_kernel<<<(batch + 255) / 256, 256, 0, st>>>(s, key, id, holes, surv);
-  open_sort_popped_kernel<<<(batch + 255) / 256, 256, 0, st>>>(s, popped, sorted);
+  const unsigned sort_blocks = (unsigned)((batch + 255) / 256);
+  open_sort_count_kernel<<<sort_blocks, 256, 0, st>>>(s, popped, ss);
+  open_sort_scan_kernel<<<1, 1024, 0, st>>>(ss);
+  open_sort_scatter_kernel<<<sort_blocks, 256, 0, st>>>(s, popped, ss, tmp);
+  open_sort_rank_kernel<<<sort_blocks, 256, 0, st>>>(s, ss, tmp, sorted);
   open_finalize_kernel<<<1, 1024, 0, st>>>(s, key, id, batch, stop_at_goal, node_solved, sorted, popped_ids);
   return dcb_check_launch();
 }

@@ -175,6 +175,8 @@ struct EpilogueArgs {
   float *out_f32;             // [M][Np] or nullptr
   const float *partial_in;    // [M][Np] fp32 partial sum of earlier K chunks (unscaled) or nullptr
   float *partial_out;         // if set: write acc (+ partial_in) here and skip the rest of the epilogue
+  const float *dot_w;         // [Np] or nullptr: fused fc_out -- dot_partial[row][n_tile] = sum over the tile's columns of out * dot_w
+  float *dot_partial;         // [M][Np/256]; the caller adds the n_tile partials in a fixed order (reproducible)
 };
 
 struct PairMaps {              // operand pairs, swept in order; the last one is the main product
@@ -208,6 +210,7 @@ __device__ __forceinline__ void prefetch_epilogue_inputs(const EpilogueArgs &ep,
 __device__ __forceinline__ void epilogue_tile(const EpilogueArgs &ep, uint32_t taddr, int64_t row0, int n0, int64_t M, int Np, int lane,
                                               uint8_t *stage_hi, uint8_t *stage_lo) {
   const int64_t row = row0 + lane;
+  float dot = 0.0f;
       const bool row_ok = row < M;
 #pragma unroll 1
 for (int c = 0; c < BN; c += 64) {
@@ -262,6 +265,11 @@ for (int c = 0; c < BN; c += 64) {
 #pragma unroll
     for (int q = 0; q < 16; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
+  if (ep.dot_w) {
+#pragma unroll
+    for (int j = 0; j < 64; j++) dot = fmaf(v[j], __ldg(ep.dot_w + n0 + c + j), dot);
+  }
+  if (!ep.out_hi) continue;
   // fp16 hi / lo split, staged (chunk q of row `lane` lives at 16-byte slot q ^ (lane & 7): conflict-free both ways)
   __syncwarp();                                  // the previous slice has been read out of the staging tile
 #pragma unroll
@@ -292,6 +300,7 @@ for (int c = 0; c < BN; c += 64) {
     }
   }
 }
+  if (ep.dot_w && row_ok) ep.dot_partial[row * (Np / BN) + n0 / BN] = dot;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -385,6 +394,7 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
       const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)buf * BN;
       const int64_t row = row0 + lane;
       const bool row_ok = row < M;
+      float dot = 0.0f;
 #pragma unroll 1
       for (int c = 0; c < BN; c += 64) {
         uint32_t acc0[32], acc1[32];
@@ -438,6 +448,11 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
 #pragma unroll
           for (int q = 0; q < 16; q++) o[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
         }
+        if (ep.dot_w) {                                // fused fc_out (pytorch_models.py:85): this row's share of the dot product
+#pragma unroll
+          for (int j = 0; j < 64; j++) dot = fmaf(v[j], __ldg(ep.dot_w + n0 + c + j), dot);
+        }
+        if (!ep.out_hi) continue;                      // last layer: only the dot product leaves the kernel (warp-uniform)
         // fp16 hi / lo split, staged (chunk q of row `lane` lives at 16-byte slot q ^ (lane & 7): conflict-free both ways)
         __syncwarp();                                  // the previous slice has been read out of the staging tile
 #pragma unroll
@@ -468,6 +483,7 @@ resnet_gemm_kernel(const __grid_constant__ PairMaps maps, int n_pairs, EpilogueA
           }
         }
       }
+      if (ep.dot_w && row_ok) ep.dot_partial[row * n_tiles + (int)(t % n_tiles)] = dot;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -698,7 +714,8 @@ bool make_map(CUtensorMap *map, const void *ptr, int64_t rows, int64_t cols, int
 
 int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const void *w_hi, const void *w_lo, int64_t ldw, const float *bias,
                        float scale, const void *skip_hi, const void *skip_lo, int relu, void *out_hi, void *out_lo, float *out_f32,
-                       const float *partial_in, float *partial_out, int64_t M, int Np, int Kp, cudaStream_t st) {
+                       const float *partial_in, float *partial_out, const float *dot_w, float *dot_partial, int64_t M, int Np, int Kp,
+                       cudaStream_t st) {
   if (M == 0) return DCB_OK;
   if (Np % BN || Kp % BK) return DCB_ERR_BAD_ARG;
   // CTA-pair (cta_group::2) kernel: DCB_GEMM_PAIR=1 always, 2 = only for launches whose epilogue neither reads a residual
@@ -720,7 +737,7 @@ int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const vo
   maps.a[n] = ma_hi; maps.w[n] = mw_hi; n++;                               // main product last
   for (int i = n; i < kMaxPairs; i++) { maps.a[i] = ma_hi; maps.w[i] = mw_hi; }
   EpilogueArgs ep{bias, scale, (const __half *)skip_hi, (const __half *)skip_lo, relu, (__half *)out_hi, (__half *)out_lo, out_f32,
-                  partial_in, partial_out};
+                  partial_in, partial_out, dot_w, dot_partial};
   static bool configured = false;
   static int sms = 148;
   if (!configured) {

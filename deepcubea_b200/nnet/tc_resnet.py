@@ -69,6 +69,10 @@ class TcResnet:
         assert w_out.shape[0] == 1
         self.w_out = w_out[0].contiguous().to(device)
         self.b_out = float(b_out[0])
+        last = self.layers[-1]
+        self.w_out_padded = torch.zeros(last.np_, dtype=torch.float32, device=device)       # fused fc_out operand (padding = 0)
+        self.w_out_padded[:last.n] = self.w_out
+        self.fuse_fc_out = __import__("os").environ.get("DCB_FUSE_FC_OUT", "1") == "1"
         self.k0 = self.layers[0].kp
         assert self.layers[0].k == self.state_dim * self.depth
         self._bufs = {}
@@ -89,7 +93,7 @@ class TcResnet:
     # the 1e-4 bar).  2048 keeps fc2 (K=5120) to three launches.  $DCB_K_CHUNK overrides for experiments.
     K_CHUNK = int(__import__('os').environ.get('DCB_K_CHUNK', 2048))
 
-    def _gemm(self, layer: _Layer, a_hi, a_lo, skip_hi, skip_lo, relu: bool, out_hi, out_lo, m: int, st: int) -> None:
+    def _gemm(self, layer: _Layer, a_hi, a_lo, skip_hi, skip_lo, relu: bool, out_hi, out_lo, m: int, st: int, dot=None) -> None:
         lib = self.lib
         use_lo = a_lo is not None and layer.w_lo is not None
         lda, ldw = a_hi.shape[1], layer.kp
@@ -107,7 +111,9 @@ class TcResnet:
                                       layer.w_hi.data_ptr() + 2 * k0, (layer.w_lo.data_ptr() + 2 * k0) if layer.w_lo is not None else None, ldw,
                                       ptr(layer.bias), layer.scale, ptr(skip_hi) if last else None, ptr(skip_lo) if last else None,
                                       1 if relu else 0, ptr(out_hi), ptr(out_lo), None,
-                                      ptr(part) if c > 0 else None, None if last else ptr(part), m, layer.np_, kc, st), "dcb_resnet_gemm")
+                                      ptr(part) if c > 0 else None, None if last else ptr(part),
+                                      ptr(dot[0]) if (dot is not None and last) else None, ptr(dot[1]) if (dot is not None and last) else None,
+                                      m, layer.np_, kc, st), "dcb_resnet_gemm")
             if self.gemm_events is not None:
                 ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
                 self.gemm_events.append((ev0, ev1, 2.0 * m * layer.n * min(kc, max(layer.k - k0, 0))))
@@ -156,9 +162,17 @@ class TcResnet:
             for k in range(self.num_blocks):
                 la, lb = self.layers[2 + 2 * k], self.layers[3 + 2 * k]
                 self._gemm(la, x_hi, x_lo, None, None, True, t_hi, t_lo, m, st)
+                if self.fuse_fc_out and k == self.num_blocks - 1:
+                    # last residual layer: fc_out (pytorch_models.py:85) is folded into its epilogue -- the [m, 1024] output never
+                    # reaches HBM, only one partial dot product per 256-column tile, added here in a fixed order
+                    dpart = self._buf32("dot_partial", m, width // 256)
+                    self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, None, None, m, st, dot=(self.w_out_padded, dpart))
+                    torch.add(dpart[:m].sum(dim=1), self.b_out, out=out[i0:i0 + m])
+                    break
                 self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, y_hi, y_lo, m, st)        # relu(fc(t) + skip)
                 x_hi, y_hi = y_hi, x_hi
                 x_lo, y_lo = y_lo, x_lo
-            check(self.lib.dcb_rowdot(ptr(x_hi), ptr(x_lo), ptr(self.w_out), self.b_out, m, self.w_out.numel(), width,
-                                      out.data_ptr() + 4 * i0, st), "dcb_rowdot")
+            else:
+                check(self.lib.dcb_rowdot(ptr(x_hi), ptr(x_lo), ptr(self.w_out), self.b_out, m, self.w_out.numel(), width,
+                                          out.data_ptr() + 4 * i0, st), "dcb_rowdot")
         return out

@@ -177,7 +177,7 @@ class BWASGpu:
             cpp = self.semantics == "cpp"
             check(lib.dcb_open_pop(ptr(self.open_state), ptr(self.open_key), ptr(self.open_id), self.open_cap, B, 1 if cpp else 0,
                                    ptr(self.node_solved), ptr(self.popped_ids), ptr(self.open_scratch), st), "open_pop")
-            self.kernel_launches += 11
+            self.kernel_launches += 14
             os_ = self._read_state()
             if os_.overflow:
                 raise _lib.DcbError("OPEN overflow: raise max_nodes (capacity %d)" % self.open_cap)

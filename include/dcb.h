@@ -201,11 +201,14 @@ int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_i
  * k_padded % 64 == 0; padding rows / cols of W and bias must be zero.
  * If d_partial_out is set the call only writes the raw fp32 sum (PARTIAL_IN + A*W) there -- used to split a long K
  * into chunks of <= 1024 chained through fp32.  Otherwise OUT is written as fp16 hi (+ lo if d_out_lo) (+ fp32 if
- * d_out_f32); relu != 0 applies max(.,0). */
+ * d_out_f32); relu != 0 applies max(.,0).
+ * Fused fc_out (pytorch_models.py:85): with d_dot_w [n_padded] set, d_dot_partial[m][n_padded/256] receives, per 256-column
+ * tile, sum_n OUT[m][n] * d_dot_w[n] in fp32 (fixed order); the caller adds the tile partials and the bias.  d_out_hi may then
+ * be NULL (nothing but the dot product leaves the kernel). */
 int dcb_resnet_gemm(const void *d_a_hi, const void *d_a_lo, int64_t lda, const void *d_w_hi, const void *d_w_lo, int64_t ldw,
                     const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
-                    void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, int64_t m,
-                    int32_t n_padded, int32_t k_padded, void *stream);
+                    void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, const float *d_dot_w,
+                    float *d_dot_partial, int64_t m, int32_t n_padded, int32_t k_padded, void *stream);
 /* F.one_hot of the nnet input (pytorch_models.py:49-52) as fp16 [m][k_padded], column = position*depth + value. */
 int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int32_t depth, int32_t k_padded, void *d_out,
                     void *stream);

@@ -35,7 +35,7 @@ def test_gemm_layer_vs_fp64(m, np_, kp, nprod):
     out_f = torch.empty((m, np_), dtype=torch.float32, device="cuda")
     p = _lib.ptr
     _lib.check(lib.dcb_resnet_gemm(p(a_hi), p(a_lo), kp, p(w_hi), p(w_lo), kp, p(bias), scale, p(s_hi), p(s_lo), 1, p(out_hi), p(out_lo), p(out_f),
-                                   None, None, m, np_, kp, torch.cuda.current_stream().cuda_stream))
+                                   None, None, None, None, m, np_, kp, torch.cuda.current_stream().cuda_stream))
     torch.cuda.synchronize()
     ref = torch.relu((a.double() @ w.double().t()) * scale + bias.double() + s_hi.double() + s_lo.double())
     err = (out_f.double() - ref).abs().max().item()
@@ -60,9 +60,9 @@ def test_gemm_k_chunks_chain_through_partial_sums():
     st = torch.cuda.current_stream().cuda_stream
     part = torch.empty((m, np_), dtype=torch.float32, device="cuda")
     o_hi = torch.empty((m, np_), dtype=torch.float16, device="cuda"); o_f = torch.empty((m, np_), dtype=torch.float32, device="cuda")
-    _lib.check(lib.dcb_resnet_gemm(p(a_hi), p(a_lo), kp, p(w_hi), p(w_lo), kp, None, 1.0, None, None, 0, None, None, None, None, p(part), m, np_, 1024, st))
+    _lib.check(lib.dcb_resnet_gemm(p(a_hi), p(a_lo), kp, p(w_hi), p(w_lo), kp, None, 1.0, None, None, 0, None, None, None, None, p(part), None, None, m, np_, 1024, st))
     _lib.check(lib.dcb_resnet_gemm(a_hi.data_ptr() + 2048, a_lo.data_ptr() + 2048, kp, w_hi.data_ptr() + 2048, w_lo.data_ptr() + 2048, kp, p(bias), 0.5,
-                                   None, None, 0, p(o_hi), None, p(o_f), p(part), None, m, np_, 1024, st))
+                                   None, None, 0, p(o_hi), None, p(o_f), p(part), None, None, None, m, np_, 1024, st))
     torch.cuda.synchronize()
     ref = (a.double() @ w.double().t()) * 0.5 + bias.double()
     assert (o_f.double() - ref).abs().max().item() < 2e-4
@@ -147,3 +147,22 @@ def test_eval_nodes_equals_gathered_input_path():
     model, _ = _model()
     tc = TcResnet(model, torch.device("cuda"), "fp16x3")
     assert torch.equal(tc.eval_nodes(0, arena, ids, 1777), tc(x))
+
+
+def test_fused_fc_out_dot_partials():
+    """dcb_resnet_gemm with d_dot_w: per-tile partial dot products of the layer output == (relu(A W^T + b + skip)) . w."""
+    from deepcubea_b200 import _lib
+    lib = _lib.load(); p = _lib.ptr
+    m, np_, kp = 1000, 1024, 1024
+    g = torch.Generator(device="cuda"); g.manual_seed(11)
+    a = torch.rand((m, kp), generator=g, device="cuda"); w = (torch.rand((np_, kp), generator=g, device="cuda") - 0.5) * 2
+    bias = torch.randn(np_, generator=g, device="cuda"); skip = torch.rand((m, np_), generator=g, device="cuda")
+    wd = torch.randn(np_, generator=g, device="cuda"); wd[1000:] = 0
+    a_hi, a_lo = _split(a); w_hi, w_lo = _split(w); s_hi, s_lo = _split(skip)
+    part = torch.zeros((m, np_ // 256), dtype=torch.float32, device="cuda")
+    _lib.check(lib.dcb_resnet_gemm(p(a_hi), p(a_lo), kp, p(w_hi), p(w_lo), kp, p(bias), 1.0, p(s_hi), p(s_lo), 1, None, None, None, None, None,
+                                   p(wd), p(part), m, np_, kp, torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    out = torch.relu(a.double() @ w.double().t() + bias.double() + s_hi.double() + s_lo.double())
+    ref = (out.view(m, 4, 256) * wd.double().view(1, 4, 256)).sum(dim=2)
+    assert (part.double() - ref).abs().max().item() < 5e-4 * max(1.0, ref.abs().max().item())
