@@ -57,34 +57,33 @@ class Environment(ABC):
         pass
 
     def generate_states(self, num_states: int, backwards_range: Tuple[int, int]) -> Tuple[List[State], List[int]]:
-        """Scramble from the goal by random reverse moves (environment_abstract.py:88-125); the numpy / `random`
-        call sequence is the reference's, so fixed seeds give the reference's states."""
-        assert num_states > 0 and backwards_range[0] >= 0
+        """Scramble goal states with random reverse moves; each state gets a depth drawn uniformly from
+        [backwards_range[0], backwards_range[1]].  Draws from numpy's and `random`'s global generators in the order the
+        reference does (environment_abstract.py:88-125), so a fixed seed yields the reference's states."""
+        lo, hi = backwards_range
+        if num_states <= 0 or lo < 0:
+            raise AssertionError("num_states must be positive and the scramble range non-negative")
         assert self.fixed_actions, "Environments without fixed actions must implement their own method"
-        depths = list(range(backwards_range[0], backwards_range[1] + 1))
-        n_moves = self.get_num_moves()
-        states: List[State] = self.generate_goal_states(num_states)
-        scramble_nums = np.random.choice(depths, num_states)
-        done_moves = np.zeros(num_states)
-        while np.max(done_moves < scramble_nums):
-            idxs = np.where(done_moves < scramble_nums)[0]
-            idxs = np.random.choice(idxs, int(max(len(idxs) / n_moves, 1)))
-            move = randrange(n_moves)
-            moved = self.prev_state([states[i] for i in idxs], move)
-            for k, s in enumerate(moved):
-                states[idxs[k]] = s
-            done_moves[idxs] = done_moves[idxs] + 1
-        return states, scramble_nums.tolist()
+        n_actions = self.get_num_moves()
+        population: List[State] = self.generate_goal_states(num_states)
+        target_depth = np.random.choice(np.arange(lo, hi + 1).tolist(), num_states)
+        applied = np.zeros(num_states)
+        pending = applied < target_depth
+        while pending.max():
+            candidates = np.flatnonzero(pending)
+            picked = np.random.choice(candidates, int(max(len(candidates) / n_actions, 1)))
+            action = randrange(n_actions)
+            for slot, moved in zip(picked, self.prev_state([population[i] for i in picked], action)):
+                population[slot] = moved
+            applied[picked] = applied[picked] + 1
+            pending = applied < target_depth
+        return population, target_depth.tolist()
 
     def expand(self, states: List[State]) -> Tuple[List[List[State]], List[np.ndarray]]:
-        """All children of every state, move-minor (environment_abstract.py:127-163)."""
+        """Children of every state for every action (action-minor) and the matching transition costs
+        (environment_abstract.py:127-163).  Concrete environments override this with one fused GPU launch."""
         assert self.fixed_actions, "Environments without fixed actions must implement their own method"
-        n, n_moves = len(states), self.get_num_moves()
-        children: List[List[State]] = [[] for _ in range(n)]
-        tc = np.empty([n, n_moves])
-        for move in range(n_moves):
-            nxt, tc_move = self.next_state(states, move)
-            tc[:, move] = np.array(tc_move)
-            for i in range(n):
-                children[i].append(nxt[i])
-        return children, [tc[i] for i in range(n)]
+        per_action = [self.next_state(states, action) for action in range(self.get_num_moves())]
+        children = [[nxt[i] for nxt, _ in per_action] for i in range(len(states))]
+        costs = np.array([tc for _, tc in per_action], dtype=np.float64).T.reshape(len(states), len(per_action))
+        return children, [costs[i] for i in range(len(states))]

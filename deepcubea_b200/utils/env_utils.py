@@ -1,22 +1,38 @@
-"""Name -> environment registry (utils/env_utils.py:6-28), restricted to the environments of the hot path."""
+"""Environment registry: name -> Environment (the reference's utils/env_utils.py:6-28 for the environments of the hot path)."""
+from __future__ import annotations
+
 import math
 import re
+from typing import Callable, List, Tuple
 
 from ..environments.environment_abstract import Environment
 
 
+def _cube3(_m) -> Environment:
+    from ..environments.cube3 import Cube3
+    return Cube3()
+
+
+def _n_puzzle(m) -> Environment:
+    from ..environments.n_puzzle import NPuzzle
+    tiles = int(m.group(1))                                  # "puzzle15" -> 15 tiles -> 4 x 4 board
+    return NPuzzle(int(math.sqrt(tiles + 1)))
+
+
+def _lights_out(m) -> Environment:
+    from ..environments.lights_out import LightsOut
+    return LightsOut(int(m.group(1)))
+
+
+_REGISTRY: List[Tuple[str, Callable]] = [(r"^cube3$", _cube3), (r"puzzle(\d+)", _n_puzzle), (r"lightsout(\d+)", _lights_out)]
+
+
 def get_environment(env_name: str) -> Environment:
-    name = env_name.lower()
-    m = re.search(r"puzzle(\d+)", name)
-    if name == "cube3":
-        from ..environments.cube3 import Cube3
-        return Cube3()
-    if m is not None:
-        from ..environments.n_puzzle import NPuzzle
-        return NPuzzle(int(math.sqrt(int(m.group(1)) + 1)))
-    if "lightsout" in name:
-        from ..environments.lights_out import LightsOut
-        return LightsOut(int(re.search(r"lightsout(\d+)", name).group(1)))
-    if name == "sokoban":
-        raise ValueError("%s is outside the B200 hot path (cube3, puzzle15/24/35/48, lightsout7)" % env_name)
+    key = env_name.lower()
+    for pattern, factory in _REGISTRY:
+        hit = re.search(pattern, key)
+        if hit:
+            return factory(hit)
+    if key == "sokoban":
+        raise ValueError("sokoban is outside the B200 hot path (cube3, puzzle15/24/35/48, lightsout7)")
     raise ValueError("No known environment %s" % env_name)

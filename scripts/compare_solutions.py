@@ -1,5 +1,5 @@
-"""Compare two results.pkl files: times, solution lengths, nodes generated, nodes/sec, % equal length
-(the reference's scripts/compare_solutions.py; Nodes/Sec here is the metric BASELINE.json quotes)."""
+"""Side-by-side statistics of two results.pkl files (the reference's scripts/compare_solutions.py): solve times, solution
+lengths, nodes generated, nodes per second -- the metric BASELINE.json quotes -- and how often the two agree on length."""
 import os
 import pickle
 import sys
@@ -7,45 +7,37 @@ from argparse import ArgumentParser
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))   # results hold environments.* State objects
 
 
-def print_stats(data, hist=False):
-    data = np.asarray(data, dtype=np.float64)
-    print("Min/Max/Median/Mean(Std) %f/%f/%f/%f(%f)" % (data.min(), data.max(), float(np.median(data)), float(data.mean()),
-                                                        float(data.std())))
-    if hist:
-        counts, edges = np.histogram(data)
-        for c, e in zip(counts, edges):
-            print("%s %s" % (c, e))
+def summary(values) -> str:
+    v = np.asarray(values, dtype=np.float64)
+    return "Min/Max/Median/Mean(Std) %f/%f/%f/%f(%f)" % (v.min(), v.max(), np.median(v), v.mean(), v.std())
 
 
-def print_results(results):
-    times = np.array(results["times"])
-    lens = np.array([len(x) for x in results["solutions"]])
-    nodes = np.array(results["num_nodes_generated"])
-    for title, arr in (("-Times-", times), ("-Lengths-", lens), ("-Nodes Generated-", nodes), ("-Nodes/Sec-", nodes / times)):
-        print(title)
-        print_stats(arr)
+def describe(results) -> None:
+    seconds = np.asarray(results["times"], dtype=np.float64)
+    nodes = np.asarray(results["num_nodes_generated"], dtype=np.float64)
+    lengths = [len(s) for s in results["solutions"]]
+    for title, column in (("Times", seconds), ("Lengths", lengths), ("Nodes Generated", nodes), ("Nodes/Sec", nodes / seconds)):
+        print("-%s-" % title)
+        print(summary(column))
 
 
 def main():
-    parser = ArgumentParser()
-    parser.add_argument("--soln1", type=str, required=True)
-    parser.add_argument("--soln2", type=str, required=True)
-    args = parser.parse_args()
-    r1 = pickle.load(open(args.soln1, "rb"))
-    r2 = pickle.load(open(args.soln2, "rb"))
-    lens1 = np.array([len(x) for x in r1["solutions"]])
-    lens2 = np.array([len(x) for x in r2["solutions"]])
-    print("%i states" % len(r1["states"]))
-    print("\n--SOLUTION 1---")
-    print_results(r1)
-    print("\n--SOLUTION 2---")
-    print_results(r2)
+    ap = ArgumentParser()
+    ap.add_argument("--soln1", type=str, required=True)
+    ap.add_argument("--soln2", type=str, required=True)
+    opt = ap.parse_args()
+    first, second = (pickle.load(open(path, "rb")) for path in (opt.soln1, opt.soln2))
+    print("%i states" % len(first["states"]))
+    for tag, res in (("SOLUTION 1", first), ("SOLUTION 2", second)):
+        print("\n--%s---" % tag)
+        describe(res)
+    delta = np.array([len(b) - len(a) for a, b in zip(first["solutions"], second["solutions"])])
     print("\n\n------Solution 2 - Solution 1 Lengths-----")
-    print_stats(lens2 - lens1)
-    print("%.2f%% soln2 equal to soln1" % (100 * np.mean(lens2 == lens1)))
+    print(summary(delta))
+    print("%.2f%% soln2 equal to soln1" % (100.0 * np.mean(delta == 0)))
 
 
 if __name__ == "__main__":
