@@ -222,7 +222,10 @@ def run_ours(args):
                     "launches": len(gemm_ev), "avg_us": round(t_s / len(gemm_ev) * 1e6, 1), "share_of_timed_region": round(t_s * 1e3 / ms, 4),
                     "algorithmic_flops": "2*rows*N*K of the unpadded layer (29.24 MFLOP per cube3 state, SURVEY 8d), one product",
                     "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 2e-5 vs fp64) "
-                            "on tiles padded to 256x64; executed tensor work = %.0f TFLOP/s; ncu: tensor pipe active 74-81%% (profiles/resnet_gemm_r01_ncu.txt)"
+                            "on tiles padded to 256x64; executed tensor work = %.0f TFLOP/s; ncu: tensor pipe active 77-89%% (profiles/resnet_gemm_r01_ncu.txt); "
+                            "DRAM traffic per K=N=1024 launch at 131072 rows (ncu --set full): 1.03 GB without / 1.60 GB with a residual input vs "
+                            "1.08 / 1.61 GB algorithmic (A hi+lo read, out hi+lo written, residual hi+lo read) -- no re-reads; traffic is null above "
+                            "because the in-loop launches differ in row count"
                             % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1",
                                ach * (89.7 / 29.24 if args.nnet_precision == "fp16x3" else 29.9 / 29.24))}
     if rank == 0:
