@@ -17,7 +17,7 @@ template <int ENV> struct ExpandShape {
   static constexpr int W = hash_words(S);
   static constexpr int REC_BYTES = S * A;
   static constexpr int REC_WORDS = S * A / 4;
-  static constexpr int GROUP = (ENV == 0) ? 2 : 4;   // children packed per group (cube3: pairs of 108 B)
+  static constexpr int GROUP = (ENV == 0) ? 2 : (ENV == 6 ? 1 : 4);   // children packed per group (cube3: pairs of 108 B; cube4: 96 B = whole words)
   static constexpr int GROUP_WORDS = GROUP * S / 4;
   static_assert(ENV == 5 || ((S * A) % 4 == 0 && (GROUP * S) % 4 == 0), "record shape");   // Lights Out (2401-byte records) has its own kernel
 };
@@ -40,9 +40,11 @@ template <int ENV, int M0, int G, class Sink> struct ExpandGroup {
       ChildOf<ENV, M0 + I, Sh::W>::apply(p, zm, ch[I]);
       const uint64_t h = state_hash<Sh::W>(ch[I]);
       sink.template store_hash<M0 + I>(h);
-      // is_solved: a solved child must hash to the goal's hash; verify the (rare) candidates exactly
+      // is_solved: a solved child must hash to the goal's hash; verify the (rare) candidates exactly.  Environments with
+      // many solved states (cube4) are tested directly.
       bool solved = false;
-      if (h == goal_hash) solved = is_goal<ENV, Sh::W>(ch[I]);
+      if constexpr (!GoalTraits<ENV>::kGoalIsUnique) solved = is_goal<ENV, Sh::W>(ch[I]);
+      else if (h == goal_hash) solved = is_goal<ENV, Sh::W>(ch[I]);
       sink.template store_solved<M0 + I>(solved);
       expand_children<I + 1>(p, zm, goal_hash, ch, sink);
     }

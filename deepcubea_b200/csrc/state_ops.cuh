@@ -5,6 +5,7 @@
 // application never indexes registers dynamically.
 #pragma once
 #include "cube3_moves.cuh"
+#include "cube4_moves.cuh"
 #include "intrinsics.cuh"
 
 namespace dcb {
@@ -18,6 +19,7 @@ template <> struct EnvTraits<2> { static constexpr int S = 25, A = 4, DIM = 5; s
 template <> struct EnvTraits<3> { static constexpr int S = 36, A = 4, DIM = 6; static constexpr bool kPuzzle = true; };
 template <> struct EnvTraits<4> { static constexpr int S = 49, A = 4, DIM = 7; static constexpr bool kPuzzle = true; };
 template <> struct EnvTraits<5> { static constexpr int S = 49, A = 49, DIM = 7; static constexpr bool kPuzzle = false; };   // Lights Out 7x7
+template <> struct EnvTraits<6> { static constexpr int S = 96, A = 24, DIM = 4; static constexpr bool kPuzzle = false; };   // 4x4x4 cube (cpp/environments.cpp:262-370)
 
 DCB_HOSTDEV constexpr int hash_words(int s) { return 2 * ((s + 7) / 8); }
 DCB_HOSTDEV constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) ? 2 : 1); }
@@ -28,9 +30,10 @@ DCB_HOSTDEV constexpr int gcd4(int s) { return (s % 4 == 0) ? 4 : ((s % 2 == 0) 
 // ---------------------------------------------------------------------------------------------------
 constexpr uint64_t kHashSeed = 0x9E3779B97F4A7C15ull;
 DCB_HOSTDEV constexpr uint32_t hash_key(int i) {
-  constexpr uint32_t k[16] = {0xa82e9745u, 0x275e0ca1u, 0xa22c9073u, 0x922741ddu, 0x98b201b5u, 0xebbdc7b7u,
+  constexpr uint32_t k[24] = {0xa82e9745u, 0x275e0ca1u, 0xa22c9073u, 0x922741ddu, 0x98b201b5u, 0xebbdc7b7u,
                               0xed62b2c5u, 0xdedc17fbu, 0x963a6a25u, 0xa4b0b7d7u, 0xd613fdbfu, 0xd5658cfdu,
-                              0x6b33c2a1u, 0x7a9e4ccbu, 0x3ae98f97u, 0x6d554fd7u};
+                              0x6b33c2a1u, 0x7a9e4ccbu, 0x3ae98f97u, 0x6d554fd7u, 0x984ad69du, 0x7f654559u,
+                              0xcae5c8b1u, 0x589234d5u, 0x6dd827ffu, 0x8e496109u, 0xc5e648bbu, 0x99730cdbu};
   return k[i];
 }
 
@@ -42,7 +45,7 @@ DCB_HOSTDEV uint64_t fmix64(uint64_t h) {
 }
 
 template <int W> DCB_DEV uint64_t state_hash(const uint32_t (&w)[W]) {
-  static_assert(W % 2 == 0 && W <= 16, "hash words");
+  static_assert(W % 2 == 0 && W <= 24, "hash words");
   uint64_t acc = kHashSeed;
 #pragma unroll
   for (int i = 0; i < W; i += 2)
@@ -55,7 +58,8 @@ template <int W> DCB_DEV uint64_t state_hash(const uint32_t (&w)[W]) {
 // ---------------------------------------------------------------------------------------------------
 template <int ENV> DCB_HOSTDEV constexpr uint8_t goal_byte(int j) {
   // cube3: sticker identity (cube3.py:37, :71-75).  n-puzzle: [1..n*n-1, 0] (n_puzzle.py:41).  Lights Out: all off.
-  return ENV == 0 ? (uint8_t)j : (ENV == 5 ? (uint8_t)0 : (uint8_t)((j + 1) % EnvTraits<ENV>::S));
+  // cube4: sticker identity (one of its many solved states, see is_goal<6>).
+  return (ENV == 0 || ENV == 6) ? (uint8_t)j : (ENV == 5 ? (uint8_t)0 : (uint8_t)((j + 1) % EnvTraits<ENV>::S));
 }
 template <int ENV> DCB_HOSTDEV constexpr uint32_t goal_word(int w) {
   constexpr int S = EnvTraits<ENV>::S;
@@ -66,10 +70,23 @@ template <int ENV> DCB_HOSTDEV constexpr uint32_t goal_word(int w) {
   }
   return v;
 }
+// kGoalIsUnique: one solved state, so "hash equals the goal's hash" pre-filters the exact compare.  The 4x4x4 cube is
+// solved when every face shows one colour = sticker id / 16 (Cube4::isSolved, cpp/environments.cpp:356-366): whole-cube
+// rotations and stickers exchanged inside a face count too, so it is tested directly on the high nibbles.
+template <int ENV> struct GoalTraits { static constexpr bool kGoalIsUnique = ENV != 6; };
 template <int ENV, int W> DCB_DEV bool is_goal(const uint32_t (&w)[W]) {
   uint32_t diff = 0;
+  if constexpr (ENV == 6) {
 #pragma unroll
-  for (int i = 0; i < W; i++) diff |= w[i] ^ goal_word<ENV>(i);
+    for (int f = 0; f < 6; f++) {
+      const uint32_t colour = (w[4 * f] & 0xF0u) * 0x01010101u;        // byte 0's colour nibble in all four bytes
+#pragma unroll
+      for (int k = 0; k < 4; k++) diff |= (w[4 * f + k] & 0xF0F0F0F0u) ^ colour;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < W; i++) diff |= w[i] ^ goal_word<ENV>(i);
+  }
   return diff == 0;
 }
 
@@ -188,6 +205,9 @@ template <int S, int W> DCB_DEV void lo_words_from_bits(uint64_t bits, uint32_t 
 template <int ENV, int MOVE, int W> struct ChildOf;
 template <int MOVE> struct ChildOf<0, MOVE, 14> {
   static DCB_DEV void apply(const uint32_t (&p)[14], const uint32_t (&)[14], uint32_t (&c)[14]) { cube3_move<MOVE>(p, c); }
+};
+template <int MOVE> struct ChildOf<6, MOVE, 24> {
+  static DCB_DEV void apply(const uint32_t (&p)[24], const uint32_t (&)[24], uint32_t (&c)[24]) { cube4_move<MOVE>(p, c); }
 };
 template <int ENV, int MOVE, int W> struct ChildOf {
   static DCB_DEV void apply(const uint32_t (&p)[W], const uint32_t (&zm)[W], uint32_t (&c)[W]) {

@@ -7,6 +7,8 @@
  *                         getNextStates: all 12 moves) + :249-256 (isSolved: state[i] == i)
  *   oracle_puzzle_expand  cpp/environments.cpp:92-113 (swap blank with swapZeroIdxs[zIdx][action])
  *                         + :119-126 (isSolved: state[i] == (i+1) % numTiles)
+ *   oracle_cube4_expand   cpp/environments.cpp:327-350 (Cube4::getNextState(s), gather form) + :356-366 (isSolved: one colour
+ *                         = id / 16 per face)
  *   oracle_hash64         project-defined hash (see oracle/oracle_env.py:state_hash64)
  */
 #include <stdint.h>
@@ -71,12 +73,28 @@ void oracle_lightsout_expand(const uint8_t *parents, int64_t n, int dim, const i
   }
 }
 
-void oracle_hash64(const uint8_t *states, int64_t n, int state_dim, const uint32_t *keys /*[16]*/,
+void oracle_cube4_expand(const uint8_t *parents, int64_t n, const int32_t *perm /*[24][96]*/, uint8_t *children /*[n][24][96]*/,
+                         uint8_t *solved /*[n][24]*/) {
+#pragma omp parallel for schedule(static)
+  for (int64_t p = 0; p < n; p++) {
+    const uint8_t *cur = parents + p * 96;
+    for (int a = 0; a < 24; a++) {
+      uint8_t *nxt = children + (p * 24 + a) * 96;
+      for (int j = 0; j < 96; j++) nxt[j] = cur[perm[a * 96 + j]];
+      uint8_t ok = 1;
+      for (int side = 0; side < 6; side++)
+        for (int i = 1; i < 16; i++) ok &= (uint8_t)(nxt[side * 16 + i] / 16 == nxt[side * 16] / 16);
+      solved[p * 24 + a] = ok;
+    }
+  }
+}
+
+void oracle_hash64(const uint8_t *states, int64_t n, int state_dim, const uint32_t *keys /*[24]*/,
                    uint64_t seed, uint64_t *out) {
   const int w = 2 * ((state_dim + 7) / 8);
 #pragma omp parallel for schedule(static)
   for (int64_t k = 0; k < n; k++) {
-    uint8_t buf[64];
+    uint8_t buf[96];
     memset(buf, 0, sizeof buf);
     memcpy(buf, states + k * state_dim, (size_t)state_dim);
     uint64_t acc = seed;

@@ -206,11 +206,64 @@ class OracleLightsOut:
         return st, scr
 
 
+class OracleCube4:
+    """cpp/environments.cpp:262-370 (the reference has no Python Cube4).  96 sticker ids, 24 quarter turns
+    (12 outer layers, then 12 inner slices); solved = every face shows one colour (state[i] / 16), environments.cpp:356-366."""
+    name = "cube4"
+    state_dim = 96
+    num_moves = 24
+
+    def __init__(self):
+        t = json.load(open(os.path.join(_GOLD, "cube4_tables.json")))
+        self.perm = np.array(t["perm"], dtype=np.int64)          # child[j] = parent[perm[a][j]] == newState[new] = state[old]
+        self.goal = np.arange(96, dtype=np.uint8)
+        self.rev_action = [a ^ 1 for a in range(24)]             # the opposite quarter turn of the same layer
+
+    def move(self, states: np.ndarray, action: int) -> np.ndarray:
+        """Cube4::getNextState (environments.cpp:327-341) in gather form."""
+        return states[:, self.perm[action]]
+
+    def prev(self, states: np.ndarray, action: int) -> np.ndarray:
+        return self.move(states, self.rev_action[action])
+
+    def is_solved(self, states: np.ndarray) -> np.ndarray:
+        """Cube4::isSolved (environments.cpp:356-366): colour = sticker id / 16, all 16 stickers of a face equal."""
+        col = (states // 16).reshape(states.shape[0], 6, 16)
+        return np.all(col == col[:, :, :1], axis=(1, 2))
+
+    def nnet_input(self, states: np.ndarray) -> np.ndarray:
+        """By analogy with cube3.py:77-85 (sticker id -> colour id); the reference ships no cube4 network."""
+        return (states // 16).astype(np.uint8)
+
+    def expand(self, states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+        ch = np.stack([self.move(states, a) for a in range(24)], axis=1)
+        return ch, np.ones((states.shape[0], 24), dtype=np.float64)
+
+    def generate_states(self, n: int, back: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:
+        """The cube3 scrambler (cube3.py:96-127) with 24 moves -- same numpy / `random` call sequence."""
+        scrambs = list(range(back[0], back[1] + 1))
+        st = np.repeat(self.goal[None, :].copy(), n, axis=0)
+        scr = np.random.choice(scrambs, n)
+        nb = np.zeros(n)
+        lt = nb < scr
+        while np.any(lt):
+            idxs = np.where(lt)[0]
+            sub = int(max(len(idxs) / 24, 1))
+            idxs = np.random.choice(idxs, sub)
+            mv = random.randrange(24)
+            st[idxs] = self.move(st[idxs], mv)
+            nb[idxs] = nb[idxs] + 1
+            lt[idxs] = nb[idxs] < scr[idxs]
+        return st, scr
+
+
 def get_oracle_env(name: str):
-    """utils/env_utils.py:6-28 (cube3, puzzle(\\d+), lightsout(\\d+))."""
+    """utils/env_utils.py:6-28 (cube3, puzzle(\\d+), lightsout(\\d+)) + cube4 (parallel_weighted_astar.cpp:386)."""
     name = name.lower()
     if name == "cube3":
         return OracleCube3()
+    if name == "cube4":
+        return OracleCube4()
     if name.startswith("lightsout"):
         return OracleLightsOut(int(name[9:]))
     if name.startswith("puzzle"):
@@ -238,7 +291,7 @@ def _splitmix64_keys(n: int) -> np.ndarray:
     return np.array(out, dtype=np.uint64)
 
 
-HASH_KEYS = _splitmix64_keys(16)   # 32-bit odd keys, enough for states up to 64 bytes
+HASH_KEYS = _splitmix64_keys(24)   # 32-bit odd keys, enough for states up to 96 bytes (cube4)
 
 
 def hash_words(state_dim: int) -> int:

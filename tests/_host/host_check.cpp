@@ -75,8 +75,18 @@ extern "C" int hc_expand(int env, const uint8_t *parents, int64_t n, uint8_t *ch
     case 2: expand_env<2>(parents, n, children, solved, hash); return 0;
     case 3: expand_env<3>(parents, n, children, solved, hash); return 0;
     case 4: expand_env<4>(parents, n, children, solved, hash); return 0;
+    case 6: expand_env<6>(parents, n, children, solved, hash); return 0;
   }
   return -1;
+}
+extern "C" int hc_is_goal(int env, const uint8_t *states, int64_t n, uint8_t *out) {
+  if (env != 6) return -1;
+  for (int64_t p = 0; p < n; p++) {
+    uint32_t w[ExpandShape<6>::W];
+    load_words<6>(states, p * 96, w);
+    out[p] = is_goal<6, ExpandShape<6>::W>(w) ? 1 : 0;
+  }
+  return 0;
 }
 extern "C" int hc_next_state(int env, const uint8_t *states, int64_t n, int action, uint8_t *out) {
   switch (env) {
@@ -85,6 +95,7 @@ extern "C" int hc_next_state(int env, const uint8_t *states, int64_t n, int acti
     case 2: next_env<2>(states, n, action, out); return 0;
     case 3: next_env<3>(states, n, action, out); return 0;
     case 4: next_env<4>(states, n, action, out); return 0;
+    case 6: next_env<6>(states, n, action, out); return 0;
   }
   return -1;
 }

@@ -54,6 +54,46 @@ def test_device_math_on_host_matches_oracle(hostcheck_lib, envid, name):
         assert np.array_equal(out, env.move(st, a))
 
 
+def test_cube4_geometry_equals_reference_tables(golden_dir):
+    """24 x 96 permutation built from the 3-D embedding == the children of the identity state dumped from the compiled
+    reference Cube4 class (tests/golden/make_golden_cube4.py)."""
+    from deepcubea_b200.environments import cube4_geometry as G
+    t = json.load(open(golden_dir + "/cube4_tables.json"))
+    assert np.array_equal(G.move_permutations(), np.array(t["perm"]))
+    assert G.inverse_actions() == [a ^ 1 for a in range(24)] and len(G.MOVES) == 24
+
+
+def test_cube4_device_math_on_host_matches_oracle_and_reference(hostcheck_lib, golden_dir):
+    """cube4 PRMT networks, hash and the colour-uniformity solved test (compiled for the host from the kernels' headers) on the
+    golden parents: children sha256 and Cube4::isSolved flags of the reference itself, and the oracle on fresh scrambles."""
+    import hashlib
+    env = O.get_oracle_env("cube4")
+    g = np.load(golden_dir + "/cube4_cfg1.npz")
+    np.random.seed(5); random.seed(5)
+    st2, _ = env.generate_states(1500, (0, 6))
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    for st, golden in ((g["parents"], True), (st2, False)):
+        n = len(st)
+        buf = np.zeros(n * 96 + 8, np.uint8); buf[:n * 96] = st.reshape(-1)
+        ch = np.zeros((n, 24, 96), np.uint8); sv = np.zeros((n, 24), np.uint8); hs = np.zeros((n, 24), np.uint64)
+        assert hostcheck_lib.hc_expand(6, p(buf), ctypes.c_int64(n), p(ch), p(sv), p(hs)) == 0
+        root = np.zeros(n, np.uint8)
+        assert hostcheck_lib.hc_is_goal(6, p(buf), ctypes.c_int64(n), p(root)) == 0
+        if golden:
+            assert hashlib.sha256(ch.tobytes()).hexdigest() == str(g["children_sha256"])
+            assert np.array_equal(np.concatenate([root[:, None], sv], 1), g["solved"]) and g["solved"].sum() > 100
+        och, _ = env.expand(st)
+        assert np.array_equal(ch, och)
+        assert np.array_equal(sv.astype(bool).reshape(-1), env.is_solved(och.reshape(-1, 96)))
+        assert np.array_equal(root.astype(bool), env.is_solved(st))
+        assert np.array_equal(hs.reshape(-1), O.state_hash64(och.reshape(-1, 96)))
+    for a in range(24):
+        out = np.zeros((len(st2), 96), np.uint8)
+        buf = np.zeros(len(st2) * 96 + 8, np.uint8); buf[:len(st2) * 96] = st2.reshape(-1)
+        assert hostcheck_lib.hc_next_state(6, p(buf), ctypes.c_int64(len(st2)), a, p(out)) == 0
+        assert np.array_equal(out, env.move(st2, a))
+
+
 def test_lightsout_device_math_on_host_matches_oracle(hostcheck_lib):
     env = O.OracleLightsOut(7)
     np.random.seed(9); random.seed(9)
