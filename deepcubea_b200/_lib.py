@@ -11,7 +11,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8,
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdcb_b200.so")
 
-ENV_IDS = {"cube3": 0, "puzzle15": 1, "puzzle24": 2, "puzzle35": 3, "puzzle48": 4, "lightsout7": 5}
+ENV_IDS = {"cube3": 0, "puzzle15": 1, "puzzle24": 2, "puzzle35": 3, "puzzle48": 4, "lightsout7": 5, "cube4": 6}
 
 
 class DcbError(RuntimeError):

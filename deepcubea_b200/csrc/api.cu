@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <string.h>
 #include "cube3_moves.cuh"
+#include "cube4_moves.cuh"
 #include "dcb_internal.h"
 
 namespace dcb {
@@ -45,9 +46,9 @@ int path_device(const uint32_t *slot_parent, uint32_t goal_id, int A, int32_t ma
 using namespace dcb;
 
 namespace {
-const int kStateBytes[DCB_NUM_ENVS] = {54, 16, 25, 36, 49, 49};
-const int kNumMoves[DCB_NUM_ENVS] = {12, 4, 4, 4, 4, 49};
-const int kDim[DCB_NUM_ENVS] = {3, 4, 5, 6, 7, 7};
+const int kStateBytes[DCB_NUM_ENVS] = {54, 16, 25, 36, 49, 49, 96};
+const int kNumMoves[DCB_NUM_ENVS] = {12, 4, 4, 4, 4, 49, 24};
+const int kDim[DCB_NUM_ENVS] = {3, 4, 5, 6, 7, 7, 4};
 inline bool env_ok(int env) { return env >= 0 && env < DCB_NUM_ENVS; }
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 inline cudaStream_t S(void *s) { return reinterpret_cast<cudaStream_t>(s); }
@@ -85,7 +86,7 @@ int dcb_env_goal_state(int env, uint8_t *h_out) {
   if (!env_ok(env)) return DCB_ERR_BAD_ENV;
   if (!h_out) return DCB_ERR_BAD_ARG;
   const int s = kStateBytes[env];
-  for (int j = 0; j < s; j++) h_out[j] = env == 0 ? (uint8_t)j : (env == DCB_ENV_LIGHTSOUT7 ? (uint8_t)0 : (uint8_t)((j + 1) % s));
+  for (int j = 0; j < s; j++) h_out[j] = (env == 0 || env == DCB_ENV_CUBE4) ? (uint8_t)j : (env == DCB_ENV_LIGHTSOUT7 ? (uint8_t)0 : (uint8_t)((j + 1) % s));
   return DCB_OK;
 }
 int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems) {
@@ -95,6 +96,12 @@ int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems) {
     if (capacity_elems < 12 * 54) return DCB_ERR_BAD_ARG;
     for (int a = 0; a < 12; a++)
       for (int j = 0; j < 54; j++) h_out[a * 54 + j] = kCube3PermHost[a][j];
+    return DCB_OK;
+  }
+  if (env == DCB_ENV_CUBE4) {                   // perm[24][96], child[j] = parent[perm[a][j]] (cpp/environments.cpp:262-341 in gather form)
+    if (capacity_elems < 24 * 96) return DCB_ERR_BAD_ARG;
+    for (int a = 0; a < 24; a++)
+      for (int j = 0; j < 96; j++) h_out[a * 96 + j] = kCube4PermHost[a][j];
     return DCB_OK;
   }
   const int d = kDim[env];

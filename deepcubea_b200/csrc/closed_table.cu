@@ -134,6 +134,7 @@ int closed_insert_device(int env, void *tbl, int64_t cap, const uint8_t *arena, 
     case 3: closed_resolve_kernel<3><<<blocks, 256, 0, st>>>(t, arena, g, valid, first_id, m, slot, keep); break;
     case 4: closed_resolve_kernel<4><<<blocks, 256, 0, st>>>(t, arena, g, valid, first_id, m, slot, keep); break;
     case 5: closed_resolve_kernel<5><<<blocks, 256, 0, st>>>(t, arena, g, valid, first_id, m, slot, keep); break;
+    case 6: closed_resolve_kernel<6><<<blocks, 256, 0, st>>>(t, arena, g, valid, first_id, m, slot, keep); break;
     default: return DCB_ERR_BAD_ENV;
   }
   return dcb_check_launch();

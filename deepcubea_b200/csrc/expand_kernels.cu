@@ -79,18 +79,24 @@ __device__ __forceinline__ void team_sync(int split, int team) {
 // TEAMS staging tiles per CTA, each filled by SPLIT warps: lane l of every warp of a team owns parent l of the tile and
 // warp `member` produces children [member*A/SPLIT, (member+1)*A/SPLIT).  Splitting the 12 moves over two warps halves
 // the time a tile spends being computed, so a larger share of the SM's staging memory is in flight to HBM at any time.
-template <int ENV, bool INDEXED, int TEAMS, int SPLIT>
+//
+// PAD > 0 (cube4): a record of 2304 bytes is a multiple of 128, so with records back to back every lane's staging stores
+// would land in the same banks (32-way conflict).  The lanes' slots are then PAD bytes apart in shared memory (2320-byte
+// stride: eight lanes' 16-byte stores tile all 32 banks) and every lane ships its own record with its own bulk store -- the
+// tile is no longer one contiguous block, but 2304-byte bulk copies are still large enough for the TMA engine.
+template <int ENV, bool INDEXED, int TEAMS, int SPLIT, int PAD = 0>
 __global__ void __launch_bounds__(TEAMS * SPLIT * 32)
 expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids, int64_t n,
               uint8_t *__restrict__ children, uint8_t *__restrict__ solved, uint64_t *__restrict__ hash) {
   using Sh = ExpandShape<ENV>;
   static_assert(Sh::A % (SPLIT * Sh::GROUP) == 0, "moves must split into whole packing groups");
+  static_assert(PAD == 0 || (SPLIT == 1 && PAD % 16 == 0 && Sh::REC_BYTES % 16 == 0), "per-lane bulk stores need 16-byte records");
   extern __shared__ __align__(16) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int team = warp / SPLIT, member = warp % SPLIT;
   constexpr int kTileBytes = 32 * Sh::REC_BYTES;
-  uint8_t *tile_smem = smem_raw + team * kTileBytes;
-  uint32_t *lane_rec = reinterpret_cast<uint32_t *>(tile_smem) + lane * Sh::REC_WORDS;
+  uint8_t *tile_smem = smem_raw + team * (32 * (Sh::REC_BYTES + PAD));
+  uint32_t *lane_rec = reinterpret_cast<uint32_t *>(tile_smem + lane * (Sh::REC_BYTES + PAD));
   const bool issuer = member == 0 && lane == 0;
 
   const int64_t n_tiles = (n + 31) >> 5;
@@ -116,8 +122,12 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
     for (int k = 0; k < LoadShape<Sh::S>::NRAW; k++) raw[k] = raw_next[k];
     const uint64_t off = off_next;
     issue_loads(tile + tile_stride);
-    if (issuer) bulk_wait_read_all();      // the previous bulk store has drained this team's staging tile
-    team_sync(SPLIT, team);
+    if constexpr (PAD > 0) {
+      bulk_wait_read_all();                // this lane's previous record has left its staging slot
+    } else {
+      if (issuer) bulk_wait_read_all();    // the previous bulk store has drained this team's staging tile
+      team_sync(SPLIT, team);
+    }
     if (valid) {
       uint32_t w[Sh::W];
       align_state<Sh::S, Sh::W>(raw, (uint32_t)(off & 3), w);
@@ -131,6 +141,13 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
       else expand_parent<ENV, SmemSink<ENV>, PER, 2 * PER>(w, sink);
     }
     fence_proxy_async_smem();
+    if constexpr (PAD > 0) {
+      if (valid) {
+        bulk_store_s2g(children + p * (int64_t)Sh::REC_BYTES, reinterpret_cast<uint8_t *>(lane_rec), (uint32_t)Sh::REC_BYTES);
+        bulk_commit();
+      }
+      continue;
+    }
     team_sync(SPLIT, team);
     const int64_t rem = n - tile * 32;
     const uint32_t bytes = (uint32_t)((rem < 32 ? rem : 32) * Sh::REC_BYTES);
@@ -144,7 +161,7 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
     if (member == 0 && lane < ((bytes - bulk) >> 2))
       reinterpret_cast<uint32_t *>(gdst + bulk)[lane] = reinterpret_cast<const uint32_t *>(tile_smem + bulk)[lane];
   }
-  if (issuer) bulk_wait_read_all();
+  if (PAD > 0 || issuer) bulk_wait_read_all();
 }
 
 // ---- secondary single-state kernels (Environment.next_state / is_solved / hash / nnet input) -------
@@ -194,13 +211,14 @@ __global__ void __launch_bounds__(256) state_kernel(const uint8_t *__restrict__ 
   }
 }
 
-// nnet input: cube3 sticker id / 9 -> colour id (cube3.py:77-85); puzzles: identity (n_puzzle.py:84-89)
-template <bool DIV9> __global__ void __launch_bounds__(256) nnet_input_kernel(const uint8_t *__restrict__ in, int64_t nbytes, uint8_t *__restrict__ out) {
+// nnet input: cube3 sticker id / 9 -> colour id (cube3.py:77-85); cube4 sticker id / 16 (same rule, 16 stickers a face);
+// puzzles / Lights Out: identity (n_puzzle.py:84-89)
+template <int DIV> __global__ void __launch_bounds__(256) nnet_input_kernel(const uint8_t *__restrict__ in, int64_t nbytes, uint8_t *__restrict__ out) {
   const int64_t nvec = nbytes >> 4;
   const int64_t t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, ts = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = t0; i < nvec; i += ts) {
     uint4 v = reinterpret_cast<const uint4 *>(in)[i];
-    if (DIV9) {
+    if (DIV == 9) {
       uint32_t *x = reinterpret_cast<uint32_t *>(&v);
 #pragma unroll
       for (int k = 0; k < 4; k++) {
@@ -209,10 +227,15 @@ template <bool DIV9> __global__ void __launch_bounds__(256) nnet_input_kernel(co
         for (int b = 0; b < 4; b++) r |= ((((x[k] >> (8 * b)) & 0xFF) * 57u) >> 9) << (8 * b);   // floor(v/9), v < 64
         x[k] = r;
       }
+    } else if (DIV == 16) {
+      uint32_t *x = reinterpret_cast<uint32_t *>(&v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) x[k] = (x[k] >> 4) & 0x0F0F0F0Fu;
     }
     reinterpret_cast<uint4 *>(out)[i] = v;
   }
-  for (int64_t i = (nvec << 4) + t0; i < nbytes; i += ts) out[i] = DIV9 ? (uint8_t)((in[i] * 57u) >> 9) : in[i];
+  for (int64_t i = (nvec << 4) + t0; i < nbytes; i += ts)
+    out[i] = DIV == 9 ? (uint8_t)((in[i] * 57u) >> 9) : (DIV == 16 ? (uint8_t)(in[i] >> 4) : in[i]);
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
@@ -227,15 +250,15 @@ static int num_sms() {
   return g_num_sms;
 }
 
-template <int ENV, bool INDEXED, int TEAMS, int SPLIT>
+template <int ENV, bool INDEXED, int TEAMS, int SPLIT, int PAD = 0>
 static int launch_expand_cfg(const uint8_t *src, const uint32_t *ids, int64_t n, uint8_t *children, uint8_t *solved, uint64_t *hash,
                              cudaStream_t st) {
   using Sh = ExpandShape<ENV>;
-  constexpr int smem = TEAMS * 32 * Sh::REC_BYTES;
+  constexpr int smem = TEAMS * 32 * (Sh::REC_BYTES + PAD);
   constexpr int threads = TEAMS * SPLIT * 32;
   static bool configured = false;
   static int blocks_per_sm = 1;
-  auto kern = expand_kernel<ENV, INDEXED, TEAMS, SPLIT>;
+  auto kern = expand_kernel<ENV, INDEXED, TEAMS, SPLIT, PAD>;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return dcb_cuda_fail();
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem) != cudaSuccess) return dcb_cuda_fail();
@@ -280,6 +303,13 @@ static int launch_expand(const uint8_t *src, const uint32_t *ids, int64_t n, uin
       case 5: return launch_expand_cfg<0, INDEXED, 1, 2>(src, ids, n, children, solved, hash, st);
       default: return launch_expand_cfg<0, INDEXED, 4, 1>(src, ids, n, children, solved, hash, st);
     }
+  } else if constexpr (ENV == 6) {
+    // cube4: a 32-parent tile of records is 72 KB, so three staging tiles (216 KB) fill the SM's shared memory.
+    // DCB_CUBE4_PAD=1 selects the bank-conflict-free staging layout with one bulk store per record (see expand_kernel).
+    static int pad = -1;
+    if (pad < 0) { const char *e = getenv("DCB_CUBE4_PAD"); pad = (e && e[0] == '1') ? 1 : 0; }
+    if (pad) return launch_expand_cfg<6, INDEXED, 3, 1, 16>(src, ids, n, children, solved, hash, st);
+    return launch_expand_cfg<6, INDEXED, 3, 1>(src, ids, n, children, solved, hash, st);
   } else {
     return launch_expand_cfg<ENV, INDEXED, 4, 1>(src, ids, n, children, solved, hash, st);
   }
@@ -295,6 +325,7 @@ static int dispatch_expand(int env, const uint8_t *src, const uint32_t *ids, int
     case 3: return launch_expand<3, INDEXED>(src, ids, n, children, solved, hash, st);
     case 4: return launch_expand<4, INDEXED>(src, ids, n, children, solved, hash, st);
     case 5: return lightsout_expand_device(src, ids, n, children, solved, hash, st);
+    case 6: return launch_expand<6, INDEXED>(src, ids, n, children, solved, hash, st);
   }
   return DCB_ERR_BAD_ENV;
 }
@@ -319,6 +350,7 @@ static int dispatch_state(int env, const uint8_t *states, int64_t n, int action,
     case 3: state_kernel<3, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     case 4: state_kernel<4, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     case 5: state_kernel<5, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
+    case 6: state_kernel<6, MODE><<<(unsigned)blocks, 256, 0, st>>>(states, n, action, out_states, out_flag, out_hash); break;
     default: return DCB_ERR_BAD_ENV;
   }
   return dcb_check_launch();
@@ -340,8 +372,9 @@ int nnet_input_device(int env, const uint8_t *states, int64_t n, uint8_t *out, c
   int64_t blocks = ((nbytes >> 4) + 255) / 256 + 1;
   const int64_t cap = (int64_t)num_sms() * 8;
   if (blocks > cap) blocks = cap;
-  if (env == 0) nnet_input_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
-  else nnet_input_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
+  if (env == 0) nnet_input_kernel<9><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
+  else if (env == DCB_ENV_CUBE4) nnet_input_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
+  else nnet_input_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(states, nbytes, out);
   return dcb_check_launch();
 }
 

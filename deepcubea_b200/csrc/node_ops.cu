@@ -31,8 +31,8 @@ compact_kept_kernel(const uint8_t *__restrict__ keep, uint32_t first_id, int64_t
   if (want) out_ids[base + __popc(mask & ((1u << lane) - 1))] = first_id + (uint32_t)i;
 }
 
-// state_to_nnet_input on gathered nodes (cube3.py:77-85 colour = sticker/9; n_puzzle.py:84-89 identity)
-template <bool DIV9>
+// state_to_nnet_input on gathered nodes (cube3.py:77-85 colour = sticker/9; cube4 sticker/16; n_puzzle.py:84-89 identity)
+template <int DIV>
 __global__ void __launch_bounds__(256)
 gather_nnet_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ ids, int64_t m, int S, uint8_t *__restrict__ out) {
   const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -40,7 +40,7 @@ gather_nnet_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict
   const int64_t j = t / S;
   const int b = (int)(t - j * S);
   const uint8_t v = arena[(uint64_t)ids[j] * S + b];
-  out[t] = DIV9 ? (uint8_t)((v * 57u) >> 9) : v;
+  out[t] = DIV == 9 ? (uint8_t)((v * 57u) >> 9) : (DIV == 16 ? (uint8_t)(v >> 4) : v);
 }
 
 // cost = h * (!solved) + weight * depth in float32, no FMA contraction (parallel_weighted_astar.cpp:298;
@@ -88,8 +88,9 @@ int gather_nnet_device(int env, const uint8_t *arena, const uint32_t *ids, int64
   if (m == 0) return DCB_OK;
   const int S = dcb_env_state_bytes(env);
   const unsigned blocks = (unsigned)((m * S + 255) / 256);
-  if (env == 0) gather_nnet_kernel<true><<<blocks, 256, 0, st>>>(arena, ids, m, S, out);
-  else gather_nnet_kernel<false><<<blocks, 256, 0, st>>>(arena, ids, m, S, out);
+  if (env == 0) gather_nnet_kernel<9><<<blocks, 256, 0, st>>>(arena, ids, m, S, out);
+  else if (env == DCB_ENV_CUBE4) gather_nnet_kernel<16><<<blocks, 256, 0, st>>>(arena, ids, m, S, out);
+  else gather_nnet_kernel<0><<<blocks, 256, 0, st>>>(arena, ids, m, S, out);
   return dcb_check_launch();
 }
 int cost_device(const float *h, const uint32_t *ids, const uint32_t *node_g, const uint8_t *node_solved, float weight,

@@ -635,8 +635,8 @@ __global__ void __launch_bounds__(256) onehot_kernel(const uint8_t *__restrict__
 }
 
 // same, reading the states of the listed nodes straight from the search's node arena (state of node i at arena + i*S):
-// state_to_nnet_input (cube3.py:77-85: sticker / 9 -> colour) and F.one_hot in one pass, no intermediate u8 matrix
-template <bool DIV9>
+// state_to_nnet_input (cube3.py:77-85: sticker / 9 -> colour; cube4: sticker / 16) and F.one_hot in one pass, no intermediate u8 matrix
+template <int DIV>
 __global__ void __launch_bounds__(256) onehot_gather_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ ids, int64_t M, int S,
                                                             int depth, int Kp, __half *__restrict__ out) {
   const int64_t total = M * (int64_t)(Kp / 8);
@@ -649,7 +649,7 @@ __global__ void __launch_bounds__(256) onehot_gather_kernel(const uint8_t *__res
     for (int e = 0; e < 8; e++) {
       const int k = k0 + e, s = k / depth, v = k - s * depth;
       int x = -1;
-      if (s < S) { x = st[s]; if (DIV9) x = (x * 57) >> 9; }
+      if (s < S) { x = st[s]; if (DIV == 9) x = (x * 57) >> 9; else if (DIV == 16) x >>= 4; }
       h[e] = (x == v) ? __float2half(1.0f) : __float2half(0.0f);
     }
     *reinterpret_cast<uint4 *>(out + m * Kp + k0) = *reinterpret_cast<const uint4 *>(h);
@@ -772,8 +772,9 @@ int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int
   if (M == 0) return DCB_OK;
   int64_t blocks = (M * (Kp / 8) + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  if (env == 0) onehot_gather_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
-  else onehot_gather_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
+  if (env == 0) onehot_gather_kernel<9><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
+  else if (env == DCB_ENV_CUBE4) onehot_gather_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
+  else onehot_gather_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
   return dcb_check_launch();
 }
 

@@ -76,8 +76,8 @@ def _device_heuristic(heuristic_fn: Callable, env: Environment) -> Callable[[tor
 
 def _env_name(env: Environment) -> str:
     kind = type(env).__name__
-    if kind == "Cube3":
-        return "cube3"
+    if kind in ("Cube3", "Cube4"):
+        return kind.lower()
     return "lightsout%d" % env.dim if kind == "LightsOut" else "puzzle%d" % (env.dim * env.dim - 1)
 
 
@@ -179,7 +179,7 @@ def main(argv: Optional[List[str]] = None):
     parser = ArgumentParser()
     parser.add_argument("--states", type=str, required=True, help="File containing states to solve")
     parser.add_argument("--model_dir", type=str, required=True, help="Directory of nnet model")
-    parser.add_argument("--env", type=str, required=True, help="Environment: cube3, puzzle15, puzzle24, puzzle35, puzzle48")
+    parser.add_argument("--env", type=str, required=True, help="Environment: cube3, cube4, puzzle15, puzzle24, puzzle35, puzzle48, lightsout7")
     parser.add_argument("--batch_size", type=int, default=1, help="Batch size for BWAS")
     parser.add_argument("--weight", type=float, default=1.0, help="Weight of path cost")
     parser.add_argument("--language", type=str, default="cuda", help="cuda (=cpp semantics on the GPU), cpp, or python")

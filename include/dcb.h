@@ -16,7 +16,7 @@
  *     per (device, stream).
  *   - return value: DCB_OK (0) or a negative DCB_ERR_* code.  Nothing throws, exits or prints.
  *   - layouts: states are packed uint8, `state_bytes` per state, no padding (cube3 54, puzzle15 16,
- *     puzzle24 25, puzzle35 36, puzzle48 49, lightsout7 49).  Children of parent p are contiguous, move-minor:
+ *     puzzle24 25, puzzle35 36, puzzle48 49, lightsout7 49, cube4 96).  Children of parent p are contiguous, move-minor:
  *     children[(p*num_moves + a)*state_bytes ...] -- the order of Environment.expand
  *     (environments/cube3.py:129-161) and of getNextStates (cpp/environments.cpp:236-243).
  */
@@ -50,7 +50,9 @@ extern "C" {
 #define DCB_ENV_PUZZLE35 3
 #define DCB_ENV_PUZZLE48 4
 #define DCB_ENV_LIGHTSOUT7 5      /* environments/lights_out.py; LightsOut in cpp/environments.cpp:133-208 */
-#define DCB_NUM_ENVS 6
+#define DCB_ENV_CUBE4 6           /* Cube4 in cpp/environments.cpp:262-370, cpp/parallel_weighted_astar.cpp:386 (C++ only in the reference;
+                                    96 sticker ids, 24 quarter turns; solved = one colour (id / 16) per face) */
+#define DCB_NUM_ENVS 7
 
 int dcb_abi_version(void);
 const char *dcb_error_string(int code);
@@ -61,10 +63,12 @@ const char *dcb_last_cuda_error(void);
 int dcb_env_num_moves(int env);
 /* bwas_cpp's state_dim table (astar.py:473-486). */
 int dcb_env_state_bytes(int env);
-/* Goal state (cube3.py:37 arange(54); n_puzzle.py:41 [1..n*n-1,0]).  h_out: state_bytes bytes. */
+/* Goal state (cube3.py:37 arange(54); n_puzzle.py:41 [1..n*n-1,0]; cube4: arange(96), one of its solved states).
+ * h_out: state_bytes bytes. */
 int dcb_env_goal_state(int env, uint8_t *h_out);
 /* The move tables the kernels were compiled with, for auditing against the reference's:
- * cube3: perm[12][54] with child[j] = parent[perm[a][j]] (cube3.py:163-171, environments.h:75-105);
+ * cube3: perm[12][54] with child[j] = parent[perm[a][j]] (cube3.py:163-171, environments.h:75-105); cube4: perm[24][96]
+ * (environments.cpp:262-341);
  * puzzles: swap_zero_idxs[n*n][4] (n_puzzle.py:174-214, environments.cpp:4-46); lightsout7: move_matrix[49][5]
  * (lights_out.py:31-42).  h_out: int32. */
 int dcb_env_move_table(int env, int32_t *h_out, int64_t capacity_elems);

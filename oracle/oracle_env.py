@@ -221,7 +221,7 @@ class OracleCube4:
 
     def move(self, states: np.ndarray, action: int) -> np.ndarray:
         """Cube4::getNextState (environments.cpp:327-341) in gather form."""
-        return states[:, self.perm[action]]
+        return np.ascontiguousarray(states[:, self.perm[action]])     # (fancy indexing alone hands back a transposed layout)
 
     def prev(self, states: np.ndarray, action: int) -> np.ndarray:
         return self.move(states, self.rev_action[action])
@@ -236,7 +236,7 @@ class OracleCube4:
         return (states // 16).astype(np.uint8)
 
     def expand(self, states: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
-        ch = np.stack([self.move(states, a) for a in range(24)], axis=1)
+        ch = np.ascontiguousarray(np.stack([self.move(states, a) for a in range(24)], axis=1))
         return ch, np.ones((states.shape[0], 24), dtype=np.float64)
 
     def generate_states(self, n: int, back: Tuple[int, int]) -> Tuple[np.ndarray, np.ndarray]:

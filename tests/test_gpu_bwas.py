@@ -22,7 +22,8 @@ def _torch_misplaced(env):
 
 @pytest.mark.parametrize("name,back,batch", [("cube3", (4, 9), 7), ("cube3", (6, 11), 100), ("cube3", (5, 8), 1),
                                               ("puzzle15", (10, 30), 50), ("puzzle24", (10, 30), 33),
-                                              ("puzzle35", (10, 30), 64), ("puzzle48", (10, 40), 20), ("lightsout7", (3, 6), 25)])
+                                              ("puzzle35", (10, 30), 64), ("puzzle48", (10, 40), 20), ("lightsout7", (3, 6), 25),
+                                              ("cube4", (3, 6), 20)])
 def test_engine_matches_oracle_trace(name, back, batch):
     from deepcubea_b200.search.bwas_gpu import BWASGpu
     env = O.get_oracle_env(name)
@@ -56,7 +57,8 @@ def test_solved_start_and_empty_solution():
 
 
 @pytest.mark.parametrize("name,back,batch,weight", [("cube3", (4, 8), 10, 1.0), ("cube3", (5, 9), 100, 0.5), ("cube3", (3, 6), 1, 1.0),
-                                                     ("puzzle15", (10, 24), 7, 0.5), ("puzzle48", (10, 30), 33, 1.0), ("lightsout7", (3, 5), 10, 0.5)])
+                                                     ("puzzle15", (10, 24), 7, 0.5), ("puzzle48", (10, 30), 33, 1.0), ("lightsout7", (3, 5), 10, 0.5),
+                                                     ("cube4", (3, 5), 10, 1.0)])
 def test_engine_python_semantics_matches_oracle_trace(name, back, batch, weight):
     """semantics="python" (the `AStar` class path, astar.py:232-340) trace-exact against oracle.bwas_python (itself pinned to
     the reference's Python AStar)."""

@@ -10,7 +10,7 @@ from oracle import oracle_env as O
 torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
-ENVS = ["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7"]
+ENVS = ["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7", "cube4"]
 
 
 def _states(name, n, seed, back):
@@ -69,6 +69,22 @@ def test_lightsout_config1_golden(golden_dir):
     assert np.array_equal(np.packbits(sv.cpu().numpy().astype(bool)), g["solved"])
 
 
+def test_cube4_config1_golden(golden_dir):
+    """4x4x4 cube: children and Cube4::isSolved flags dumped from the compiled reference class (scrambles, whole-cube
+    rotations, stickers exchanged inside a face and their neighbours); the indexed kernel is covered by tests/test_gpu_bwas.py."""
+    from deepcubea_b200 import ops
+    g = np.load(golden_dir + "/cube4_cfg1.npz")
+    par = torch.from_numpy(g["parents"]).cuda()
+    ch, sv, hs = ops.expand(6, par)
+    chn = ch.cpu().numpy()
+    assert hashlib.sha256(chn.tobytes()).hexdigest() == str(g["children_sha256"])
+    assert np.array_equal(chn[:64], g["children_head"])
+    root = ops.is_solved(6, par).cpu().numpy()
+    assert np.array_equal(np.concatenate([root[:, None], sv.cpu().numpy()], axis=1), g["solved"])
+    assert np.array_equal(hs.cpu().numpy().reshape(-1).view(np.uint64), O.state_hash64(chn.reshape(-1, 96)))
+    assert np.array_equal(ops.nnet_input(6, par).cpu().numpy(), g["parents"] // 16)
+
+
 @pytest.mark.parametrize("name", ["cube3", "puzzle15", "puzzle48", "lightsout7"])
 def test_golden_triples(golden_dir, name):
     """Every (s, a, s') of the reference's shipped BWAS results replays bit-exactly through next_state."""
@@ -96,7 +112,7 @@ def test_single_state_ops(name):
     for a in range(env.num_moves):
         assert np.array_equal(ops.next_state(eid, d, a).cpu().numpy(), env.move(st, a))
         back = ops.next_state(eid, ops.next_state(eid, d, a), env.rev_action[a]).cpu().numpy()
-        if name in ("cube3", "lightsout7"):
+        if name in ("cube3", "lightsout7", "cube4"):
             assert np.array_equal(back, st)       # move then inverse = identity
     assert np.array_equal(ops.is_solved(eid, d).cpu().numpy().astype(bool), env.is_solved(st))
     assert np.array_equal(ops.hash_states(eid, d).cpu().numpy().view(np.uint64), O.state_hash64(st))

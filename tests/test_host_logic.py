@@ -149,6 +149,14 @@ def test_abi_tables_match_reference(golden_dir):
     assert np.array_equal(buf.reshape(49, 5), np.array(lo["move_matrix"]))
     goal = np.ones(49, np.uint8)
     assert lib.dcb_env_goal_state(5, _lib.ptr(goal)) == 0 and goal.sum() == 0
+    c4 = json.load(open(golden_dir + "/cube4_tables.json"))
+    buf = np.zeros(24 * 96, np.int32)
+    assert lib.dcb_env_move_table(6, _lib.ptr(buf), buf.size) == 0 and lib.dcb_env_move_table(6, _lib.ptr(buf), 100) < 0
+    assert np.array_equal(buf.reshape(24, 96), np.array(c4["perm"]))
+    goal = np.zeros(96, np.uint8)
+    assert lib.dcb_env_goal_state(6, _lib.ptr(goal)) == 0 and np.array_equal(goal, np.arange(96))
+    assert (lib.dcb_env_state_bytes(6), lib.dcb_env_num_moves(6), lib.dcb_env_slot_align(6)) == (96, 24, 1)
+    assert lib.dcb_env_state_bytes(7) < 0
 
 
 def test_product_fails_loudly_without_gpu():
@@ -179,7 +187,8 @@ def test_product_never_imports_oracle():
 def test_registry_and_plugin_api_surface():
     from deepcubea_b200.environments.environment_abstract import Environment
     from deepcubea_b200.utils.env_utils import get_environment
-    for name, S, A in (("cube3", 54, 12), ("puzzle15", 16, 4), ("PUZZLE24", 25, 4), ("puzzle35", 36, 4), ("puzzle48", 49, 4), ("lightsout7", 49, 49)):
+    for name, S, A in (("cube3", 54, 12), ("puzzle15", 16, 4), ("PUZZLE24", 25, 4), ("puzzle35", 36, 4), ("puzzle48", 49, 4), ("lightsout7", 49, 49),
+                       ("cube4", 96, 24)):
         env = get_environment(name)
         assert isinstance(env, Environment) and env.get_num_moves() == A and env.state_dim == S
         for m in ("next_state", "prev_state", "generate_goal_states", "is_solved", "state_to_nnet_input", "get_nnet_model",
@@ -188,7 +197,7 @@ def test_registry_and_plugin_api_surface():
         goals = env.generate_goal_states(3)
         assert len({hash(g) for g in goals}) == 1 and goals[0] == goals[1]
         assert env.generate_goal_states(2, np_format=True).shape == (2, S)
-    for bad in ("lightsout5", "sokoban", "cube4"):
+    for bad in ("lightsout5", "sokoban", "cube5"):
         with pytest.raises(ValueError):
             get_environment(bad)
     env = get_environment("puzzle15")

@@ -23,7 +23,7 @@ def _tie_free(env):
 
 @pytest.mark.skipif(not have_reference_binary(), reason="oracle/_ref/parallel_weighted_astar not built (needs /root/reference)")
 @pytest.mark.parametrize("name,back,batch,weight", [("cube3", (4, 8), 100, 0.8), ("cube3", (5, 9), 10, 0.6), ("cube3", (3, 6), 1, 1.0),
-                                                     ("puzzle15", (10, 24), 20, 0.8), ("puzzle48", (8, 16), 50, 0.6)])
+                                                     ("puzzle15", (10, 24), 20, 0.8), ("puzzle48", (8, 16), 50, 0.6), ("cube4", (3, 6), 20, 0.8)])
 def test_oracle_bwas_equals_reference_binary(name, back, batch, weight):
     env = O.get_oracle_env(name)
     h = _tie_free(env)

@@ -91,7 +91,26 @@ def test_shipped_optimal_solutions_solve(golden_dir, name):
     assert env.is_solved(st).all()
 
 
-@pytest.mark.parametrize("name", ["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48"])
+def test_cube4_oracle_reproduces_reference(golden_dir):
+    """4x4x4 cube (SURVEY 8f rank 4; C++-only in the reference): the 24 permutations, all children and Cube4::isSolved of 1564
+    parents -- scrambles, whole-cube rotations, stickers exchanged inside a face and their neighbours -- as dumped from the
+    compiled reference class (tests/golden/make_golden_cube4.py)."""
+    env = O.get_oracle_env("cube4")
+    t = json.load(open(golden_dir + "/cube4_tables.json"))
+    perm = np.array(t["perm"])
+    assert perm.shape == (24, 96) and all(sorted(r) == list(range(96)) for r in perm.tolist())
+    assert [int((r != np.arange(96)).sum()) for r in perm] == [32] * 12 + [16] * 12        # outer layers, inner slices
+    g = np.load(golden_dir + "/cube4_cfg1.npz")
+    ch, _ = env.expand(g["parents"])
+    assert _sha(ch) == str(g["children_sha256"]) and np.array_equal(ch[:64], g["children_head"])
+    sol = np.concatenate([env.is_solved(g["parents"])[:, None], env.is_solved(ch.reshape(-1, 96)).reshape(-1, 24)], axis=1)
+    assert np.array_equal(sol, g["solved"].astype(bool)) and sol.sum() == int(g["n_solved"]) > 100
+    assert sol[:, 0].sum() > 10 and not np.array_equal(g["parents"][sol[:, 0]][-1], env.goal)  # solved, yet not the identity state
+    for a in range(24):
+        assert np.array_equal(env.prev(env.move(g["parents"], a), a), g["parents"])
+
+
+@pytest.mark.parametrize("name", ["cube3", "cube4", "puzzle15", "puzzle24", "puzzle35", "puzzle48"])
 def test_c_oracle_equals_numpy_oracle(oracle_clib, golden_dir, name):
     env = O.get_oracle_env(name)
     np.random.seed(4); random.seed(4)
@@ -103,6 +122,9 @@ def test_c_oracle_equals_numpy_oracle(oracle_clib, golden_dir, name):
         t = json.load(open(golden_dir + "/cube3_tables.json"))
         new, old = np.array(t["idxs_new"], np.int32), np.array(t["idxs_old"], np.int32)
         oracle_clib.oracle_cube3_expand(p(st), ctypes.c_int64(n), p(new), p(old), p(ch), p(sv))
+    elif name == "cube4":
+        perm = np.ascontiguousarray(env.perm, dtype=np.int32)
+        oracle_clib.oracle_cube4_expand(p(st), ctypes.c_int64(n), p(perm), p(ch), p(sv))
     else:
         sw = np.ascontiguousarray(env.swap, dtype=np.int32)
         oracle_clib.oracle_puzzle_expand(p(st), ctypes.c_int64(n), env.dim, p(sw), p(ch), p(sv))

@@ -12,7 +12,10 @@ except Exception:
     peak, src = 6650.0, "fallback"
 print("# expand + is_solved + hash kernel, one launch, CUDA events (median of 8 after 4 warm-ups); peak = %.1f GB/s (%s copy bandwidth)" % (peak, src))
 print("%-11s %10s %6s %4s %12s %10s %12s %8s" % ("env", "parents", "S", "A", "B/child", "us", "GB/s (alg.)", "frac"))
-for env, name in enumerate(["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7"]):
+only = os.environ.get("DCB_BENCH_ENVS")          # e.g. "cube4" to time one environment
+for env, name in enumerate(["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7", "cube4"]):
+    if only and name not in only.split(","):
+        continue
     S, A = ops.env_shape(env)
     alg = S / A + S + 1 + 8
     n = int(min(1 << 23, (1.6e9 // (A * S)) // 1024 * 1024))

@@ -1,4 +1,6 @@
 cd $GRAFT_REPO_ROOT
-for p in 0 2; do echo "== DCB_GEMM_PAIR=$p"; DCB_GEMM_PAIR=$p timeout 120 python tools/bench_nnet.py 2>&1 | tail -2; done
-DCB_GEMM_PAIR=2 timeout 300 python -m pytest tests/test_gpu_nnet.py -x -q -m gpu 2>&1 | tail -2
-for p in 2 0; do echo "== bench DCB_GEMM_PAIR=$p"; DCB_GEMM_PAIR=$p timeout 200 python bench.py 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['roofline'])"; done
+echo "== cube4 default"; timeout 200 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_bwas.py -x -q -m gpu -k cube4 2>&1 | tail -3
+echo "== cube4 padded staging"; DCB_CUBE4_PAD=1 timeout 200 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_bwas.py -x -q -m gpu -k cube4 2>&1 | tail -3
+echo "== timing"; DCB_BENCH_ENVS=cube4,cube3 timeout 100 python tools/bench_expand_envs.py 2>&1 | tail -3
+DCB_CUBE4_PAD=1 DCB_BENCH_ENVS=cube4 timeout 100 python tools/bench_expand_envs.py 2>&1 | tail -1
+echo "== regression"; timeout 400 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_nnet.py tests/test_gpu_closed_open.py tests/test_gpu_bwas.py -x -q -m gpu 2>&1 | tail -3

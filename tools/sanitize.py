@@ -9,7 +9,7 @@ from deepcubea_b200.search.bwas_gpu import BWASGpu
 from deepcubea_b200.utils.pytorch_models import ResnetModel
 lib = _lib.load()
 g = torch.Generator(device="cuda"); g.manual_seed(0)
-for env, name in enumerate(["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7"]):
+for env, name in enumerate(["cube3", "puzzle15", "puzzle24", "puzzle35", "puzzle48", "lightsout7", "cube4"]):
     S, A = ops.env_shape(env)
     goal = torch.zeros(S, dtype=torch.uint8); _lib.check(lib.dcb_env_goal_state(env, goal.data_ptr()))
     st = goal.cuda().repeat(333, 1)
