@@ -1,6 +1,4 @@
 cd $GRAFT_REPO_ROOT
-echo "== cube4 default"; timeout 200 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_bwas.py -x -q -m gpu -k cube4 2>&1 | tail -3
-echo "== cube4 padded staging"; DCB_CUBE4_PAD=1 timeout 200 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_bwas.py -x -q -m gpu -k cube4 2>&1 | tail -3
-echo "== timing"; DCB_BENCH_ENVS=cube4,cube3 timeout 100 python tools/bench_expand_envs.py 2>&1 | tail -3
-DCB_CUBE4_PAD=1 DCB_BENCH_ENVS=cube4 timeout 100 python tools/bench_expand_envs.py 2>&1 | tail -1
-echo "== regression"; timeout 400 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_nnet.py tests/test_gpu_closed_open.py tests/test_gpu_bwas.py -x -q -m gpu 2>&1 | tail -3
+timeout 120 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 200 python -m pytest tests/test_gpu_env_step.py tests/test_gpu_bwas.py -x -q -m gpu -k cube4 2>&1 | tail -2
+timeout 300 compute-sanitizer --tool memcheck --print-limit 20 python tools/sanitize.py 2>&1 | grep -E "ERROR SUMMARY|Invalid|cube4|done" | head -8
