@@ -93,7 +93,8 @@ int dcb_expand_indexed(int env, const uint8_t *d_arena, const uint32_t *d_parent
 
 /* Environment.next_state for one action (cube3.py:48-54, n_puzzle.py:46-61; getNextState). */
 int dcb_next_state(int env, const uint8_t *d_states, int64_t n, int action, uint8_t *d_next, void *stream);
-/* Environment.is_solved (cube3.py:71-75, n_puzzle.py:78-82; isSolved). d_solved [n] u8. */
+/* Environment.is_solved (cube3.py:71-75, n_puzzle.py:78-82; isSolved). d_solved [n] u8.  cube4 follows Cube4::isSolved
+ * (environments.cpp:356-366): every face one colour (id / 16), not sticker identity. */
 int dcb_is_solved(int env, const uint8_t *d_states, int64_t n, uint8_t *d_solved, void *stream);
 /* Project-defined state hash of arbitrary states. d_hash [n] u64. */
 int dcb_hash_states(int env, const uint8_t *d_states, int64_t n, uint64_t *d_hash, void *stream);
