@@ -12,7 +12,7 @@ states, solutions, paths, times, num_nodes_generated.  --language values:
     cuda (default), cpp : GPU engine with the C++ program's semantics (cpp/parallel_weighted_astar.cpp:138-346),
                           the variant that produced the reference's shipped results;
     python              : GPU engine with the Python AStar semantics (astar.py:232-340, 400-454).
-Extra flags: --nnet_precision {fp32,tf32,bf16}, --max_nodes N.
+Extra flags: --nnet_precision {fp32,tf32,bf16,fp16x3,fp16}, --max_nodes N, --num_states N.
 """
 from __future__ import annotations
 
