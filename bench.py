@@ -1,24 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- cube3 batch-weighted-A* node expansions / second on B200 (BASELINE.json's metric).
+"""bench.py -- batch-weighted-A* node expansions / second on B200 (BASELINE.json's metric).
 
-    python bench.py --gpus N --steps K --warmup W                  # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K --warmup W  # the reference's C++ BWAS on the host cores
+    python bench.py --gpus N --steps K --warmup W                   # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's C++ BWAS on the host cores
+    python bench.py --full --num_states 1000                         # whole searches to completion (BASELINE configs[1] / [3])
+    python bench.py --workload puzzle15|puzzle48                     # BASELINE configs[2] / [4]
 
-Workload (BASELINE.json configs[1]): cube3 A*, weight 0.8, batch_size 20000, start states from the
-reference's scramble generator generate_states(n, (0, 26)) under fixed seeds.  A STEP is one BWAS iteration:
-pop <= 20000 nodes from OPEN, expand them (240k children), CLOSED insert-or-improve, cost-to-go network on the
-surviving children, push.  Steps run back to back over consecutive start states (a solved state is followed by
-the next one).  `value` = nodes generated (every child, the reference's Nodes/Sec numerator) / time.
+Workload (BASELINE.json configs[1]): cube3 A*, weight 0.8, batch_size 20000, start states from the reference's scramble
+generator generate_states(n, (0, 26)) under fixed seeds.  BOTH arms run the SAME start states under the SAME counting rule:
 
-Timed region: barrier + synchronize, K steps, synchronize + barrier; device time from CUDA events, max over ranks.
-The per-step working set (arena + CLOSED + OPEN, hundreds of MB) is larger than L2.
-One JSON line on stdout (rank 0).
+  * the bounded sample of the workload = the scrambles of depth >= 20 of that seeded list, in order (shallower scrambles are
+    solved within a few dozen children and never reach a full batch); rank r takes every world-th state starting at r;
+  * a STEP is one FULL-BATCH BWAS iteration -- pop 20000 nodes from OPEN, expand them (240000 children), CLOSED
+    insert-or-improve, cost-to-go network on the surviving children, push.  The ramp-up iterations of a search (1, 12, 132 ...
+    children) ride along inside the window when a search ends and the next state starts: their time and their nodes are counted,
+    they are not steps;
+  * `value` = nodes generated AND materialised (expanded, deduplicated, evaluated) inside the window / time.  The children of
+    an iteration that fires the termination rule are part of the reference's `num_nodes_generated` but this engine never
+    materialises them: they are NOT in the numerator.
+  * warm-up = the iterations up to and including the W-th full-batch one.
+
+Timed region: barrier + synchronize, K steps, synchronize + barrier; device time from CUDA events, max over ranks.  The per-step
+working set (arena + CLOSED + OPEN, hundreds of MB) is larger than L2.  `full_search` in the line = whole searches run to
+completion right after the window (the steady-state number the window slightly overstates).  One JSON line on stdout (rank 0).
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import pickle
 import random
 import subprocess
 import sys
@@ -30,12 +41,27 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "cube3_astar_node_expansions_per_sec"
 UNIT = "nodes/s"
-WEIGHT, BATCH = 0.8, 20000
-ALG_BYTES_PER_CHILD = 54.0 / 12 + 54 + 1 + 8          # expand + is_solved + hash, unpadded
-WEIGHTS = os.path.join(ROOT, "assets", "saved_models", "cube3", "current", "model_state_dict.pt")
+BATCH = 20000
+MIN_SCRAMBLE = 20
+SEED = 1234
+POOL = 1024                                            # size of the seeded scramble list both arms draw from
 NCU_TRAFFIC_BYTES = 116.28e6 + 1527.19e6               # ncu --set full, expand_kernel<cube3>, 2^21 parents (profiles/expand_r01_ncu.txt)
+
+# per workload: env name, weight, state bytes, moves, MFLOP per state of the cost-to-go net, BASELINE config
+WORKLOADS = {
+    "cube3": dict(env="cube3", weight=0.8, S=54, A=12, mflop=29.24, config="cube3 A* weight=0.8 batch_size=20000, scrambles depth<=26 (BASELINE configs[1])"),
+    "puzzle15": dict(env="puzzle15", weight=0.8, S=16, A=4, mflop=28.56, config="puzzle15 A* weight=0.8 batch_size=20000 on data/puzzle15/test (BASELINE configs[2])"),
+    "puzzle48": dict(env="puzzle48", weight=0.8, S=49, A=4, mflop=50.01, config="puzzle48 A* weight=0.8 batch_size=20000 on data/puzzle48/test (BASELINE configs[4])"),
+}
+
+
+def metric_name(wl):
+    return "%s_astar_node_expansions_per_sec" % wl
+
+
+def weights_path(env):
+    return os.path.join(ROOT, "assets", "saved_models", env, "current", "model_state_dict.pt")
 
 
 def measured_peaks():
@@ -58,7 +84,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -87,25 +113,53 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_states(n: int, seed: int) -> np.ndarray:
-    """Synthetic start states: the reference generator's semantics (environments/cube3.py:96-127), run by this
-    repo's GPU-backed environment."""
-    from deepcubea_b200.utils.env_utils import get_environment
-    env = get_environment("cube3")
-    np.random.seed(seed); random.seed(seed)
-    states, _ = env.generate_states(n, (0, 26))
-    return env.pack(states)
+# =====================================================================================================
+# the workload's start states -- ONE definition for both arms
+# =====================================================================================================
+def workload_states(wl: str, n: int, full: bool = False):
+    """u8 [n, S] start states + a description.  cube3: the reference generator's semantics (environments/cube3.py:96-127)
+    restated by the oracle's numpy port (identical to the GPU-backed environment, tests/test_gpu_cli.py); the puzzles use the
+    reference's own test files (assets/, copied by tools/fetch_assets.py)."""
+    w = WORKLOADS[wl]
+    if wl == "cube3":
+        import torch
+        if torch.cuda.is_available():           # the product's GPU-backed environment (same RNG call order as the reference)
+            from deepcubea_b200.utils.env_utils import get_environment
+            env = get_environment("cube3")
+            gen = lambda k: (lambda st, d: (env.pack(st), d))(*env.generate_states(k, (0, 26)))
+        else:                                   # reference arm on a GPU-less host: the checker's numpy port of the same generator
+            from oracle import oracle_env as O
+            gen = lambda k: O.OracleCube3().generate_states(k, (0, 26))
+        pool = n if full else POOL
+        while True:
+            np.random.seed(SEED); random.seed(SEED)
+            states, depths = gen(pool)
+            if full:
+                return states[:n], "generate_states(%d,(0,26)), seed %d, every state" % (n, SEED)
+            keep = np.nonzero(np.asarray(depths) >= MIN_SCRAMBLE)[0]
+            if len(keep) >= n:
+                return states[keep[:n]], "generate_states(%d,(0,26)), seed %d, scramble depth >= %d kept, first %d in order" % (pool, SEED, MIN_SCRAMBLE, n)
+            pool *= 8                            # fixed tiers, so both arms always draw from the same list
+    path = os.path.join(ROOT, "assets", "data", w["env"], "test", "data_0.pkl")
+    if not os.path.exists(path):
+        raise RuntimeError("%s missing: run tools/fetch_assets.py %s where /root/reference exists" % (path, w["env"]))
+    sys.path.insert(0, ROOT)
+    data = pickle.load(open(path, "rb"))
+    attr = "tiles"
+    arr = np.stack([np.asarray(getattr(s, attr), dtype=np.uint8) for s in data["states"][:n]])
+    return arr, "first %d states of data/%s/test/data_0.pkl" % (len(arr), w["env"])
 
 
-def build_heuristic(device, precision: str):
+def build_heuristic(wl, device, precision: str):
     import torch
     from deepcubea_b200.nnet.folded import DeviceHeuristic, FoldedResnet
     from deepcubea_b200.utils.env_utils import get_environment
     from deepcubea_b200.utils.nnet_utils import load_nnet
-    env = get_environment("cube3")
+    env = get_environment(WORKLOADS[wl]["env"])
     model = env.get_nnet_model()
-    if os.path.exists(WEIGHTS):
-        load_nnet(WEIGHTS, model, device=torch.device("cpu"))
+    wp = weights_path(WORKLOADS[wl]["env"])
+    if os.path.exists(wp):
+        load_nnet(wp, model, device=torch.device("cpu"))
         src = "trained weights (assets/)"
     else:
         torch.manual_seed(0)
@@ -120,6 +174,25 @@ def build_heuristic(device, precision: str):
     return DeviceHeuristic(FoldedResnet(model, mode=precision).to(device), chunk=1 << 17), src
 
 
+class InstanceQueue:
+    """Dynamic whole-instance queue across ranks: an atomic fetch-add on the job's c10d store (host side, ~0.1 ms per
+    instance, nothing on the data path).  SURVEY 8(e): load imbalance between instances is THE scaling loss."""
+
+    def __init__(self, n_items: int, world: int):
+        self.n, self.world, self.local = n_items, world, 0
+        self.store = None
+        if world > 1:
+            import torch.distributed as dist
+            self.store = dist.distributed_c10d._get_default_store()
+
+    def next(self):
+        if self.store is None:
+            i = self.local; self.local += 1
+        else:
+            i = int(self.store.add("dcb_instance_queue", 1)) - 1
+        return i if i < self.n else None
+
+
 # =====================================================================================================
 def run_ours(args):
     import torch
@@ -127,6 +200,9 @@ def run_ours(args):
     from deepcubea_b200 import _lib, ops
     from deepcubea_b200.search.bwas_gpu import BWASGpu
     from deepcubea_b200.search import sharding
+    wl = args.workload
+    W = WORKLOADS[wl]
+    A = W["A"]
     rank, world, local = sharding.world()
     if not torch.cuda.is_available():
         raise _lib.DcbError("bench.py needs a CUDA device (no CPU fallback)")
@@ -134,38 +210,47 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    heur, weights_src = build_heuristic(dev, args.nnet_precision)
-    steps_total = args.steps + args.warmup
-    max_nodes = int(min(1 << 27, max(1 << 24, 2 * steps_total * BATCH * 12)))
-    eng = BWASGpu("cube3", heur, WEIGHT, BATCH, max_nodes=max_nodes, device=dev)
-    # instances shard by rank (instance i -> rank i % world): weak scaling, no data-path collective
-    n_inst = max(4, steps_total // 8)
-    all_states = make_states(n_inst * world, seed=1234)
-    states = all_states[sharding.shard_indices(len(all_states), rank, world)]
+    heur, weights_src = build_heuristic(wl, dev, args.nnet_precision)
+    eng = BWASGpu(W["env"], heur, W["weight"], BATCH, max_nodes=args.max_nodes, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
         sharding.completion_barrier()
 
-    def run_steps(k, cursor):
-        """k BWAS iterations over consecutive start states; returns (nodes, solved, lens, cursor)."""
-        nodes, solved, lens = 0, 0, []
-        while k > 0:
+    if args.full:
+        return run_full(args, eng, heur, rank, world, dev, weights_src, barrier)
+
+    n_inst = max(8, (args.steps + args.warmup) // 2)
+    all_states, states_desc = workload_states(wl, n_inst * world)
+    states = all_states[sharding.shard_indices(len(all_states), rank, world)]
+
+    def run_window(k_full, cursor):
+        """Search iterations over consecutive start states until k_full FULL-BATCH iterations were materialised.
+        Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
+        nodes = iters = solved = full = 0
+        lens = []
+        rows0 = eng.total_kept
+        while full < k_full:
+            if iters > 400 * max(1, k_full):
+                raise _lib.DcbError("bench window: the searches never reach full batches")
             if cursor["fresh"]:
                 eng.reset(states[cursor["i"] % len(states)]); cursor["fresh"] = False
-            before = eng.nodes_generated
-            eng.step(); k -= 1
-            nodes += eng.nodes_generated - before
+            before = eng.nodes_expanded
+            eng.step(); iters += 1
+            got = eng.nodes_expanded - before
+            nodes += got
+            if got == BATCH * A:
+                full += 1
             if not eng.done and eng.next_slot + 2 * BATCH + 64 > eng.max_slots:
-                eng.done = 3                      # arena nearly full (never with trained weights): move on to the next instance
+                eng.done = 3                      # arena nearly full: move on to the next instance
             if eng.done:
                 if eng.done == 1:
                     solved += 1; lens.append(len(eng.path_to(eng.goal_id)))
                 cursor["i"] += 1; cursor["fresh"] = True
-        return nodes, solved, lens
+        return nodes, eng.total_kept - rows0, iters, solved, lens
 
     cursor = {"i": 0, "fresh": True}
-    run_steps(args.warmup, cursor)
+    run_window(args.warmup, cursor)
     # ---- device-resident timed region ----------------------------------------------------------------
     eng.expand_events = []
     tc_heur = hasattr(heur, "gemm_events")
@@ -173,7 +258,6 @@ def run_ours(args):
         heur.gemm_events = []
         gemm0 = heur.gemm_launches
     launches0 = eng.kernel_launches
-    kept0 = eng.total_kept
     sampler = ClockSampler(local); sampler.start()
     barrier()
     prof = os.environ.get("DCB_CUDA_PROFILER") == "1"     # `ncu --profile-from-start off`: capture the timed region only
@@ -181,7 +265,7 @@ def run_ours(args):
         torch.cuda.profiler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
-    nodes, solved, lens = run_steps(args.steps, cursor)
+    nodes, kept, iters, solved, lens = run_window(args.steps, cursor)
     ev1.record()
     barrier()
     if prof:
@@ -189,46 +273,57 @@ def run_ours(args):
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = eng.kernel_launches - launches0
-    kept = eng.total_kept - kept0
     gemm_ev = []
     if tc_heur:
         gemm_ev = [(a.elapsed_time(b), f) for a, b, f in heur.gemm_events]
         heur.gemm_events = None
         n_nn = heur.gemm_launches - gemm0
-        launches += n_nn + 2 * max(1, n_nn // 14)          # + one-hot and fc_out kernels of each forward pass
+        launches += n_nn + 2 * max(1, n_nn // 10)          # + one-hot and fc_out kernels of each forward pass
     in_loop = [(a.elapsed_time(b), n) for a, b, n in eng.expand_events]
     eng.expand_events = None
     # ---- end-to-end through the public API: host start state in, host solution out ---------------------
     cursor2 = {"i": cursor["i"] + 1, "fresh": True}
+    run_window(args.warmup, cursor2)                       # this search's ramp-up (untimed, as in the device window)
     h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
     barrier()
     t0 = time.perf_counter()
-    e_nodes, _, _ = run_steps(args.steps, cursor2)
+    e_nodes, _, _, _, _ = run_window(args.steps, cursor2)
     torch.cuda.synchronize()
     e_sec = time.perf_counter() - t0
     barrier()
     h2d, d2h = eng.h2d_bytes - h2d0, eng.d2h_bytes - d2h0
-    # ---- gather-kernel roofline: streaming-size launches of the same kernel, CUDA events ------------------
+    # ---- whole searches to completion (steady state incl. ramp-up, large OPEN / CLOSED and the final iteration) ----------
+    f_nodes = f_sec = 0.0
+    f_solved, f_lens = 0, []
+    for j in range(args.full_states):
+        s = states[(cursor2["i"] + 1 + j) % len(states)]
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        try:
+            r = eng.solve(s)
+        except _lib.DcbError:
+            continue
+        f_sec += time.perf_counter() - t0
+        f_nodes += r.nodes_generated
+        if r.moves is not None:
+            f_solved += 1; f_lens.append(len(r.moves))
+    # ---- rooflines ----------------------------------------------------------------------------------------------
     peak, tc_sus, tc_burst, peak_src = measured_peaks()
-    roof = None
-    roof_dom = None
+    roof = roof_dom = None
     if rank == 0 and gemm_ev:
-        # the dominant kernel of the step (95% of device time, profiles/launches_r01_summary.txt): the tcgen05 dense layers
         t_s = sum(x[0] for x in gemm_ev) * 1e-3
         fl = sum(x[1] for x in gemm_ev)
         ach = fl / t_s / 1e12
-        roof_dom = {"kernel": "resnet_gemm_kernel (tcgen05 dense layers of the cost-to-go ResNet)", "bound": "tensor", "achieved": round(ach, 1),
-                    "peak": tc_sus, "unit": "TFLOP/s", "frac": round(ach / tc_sus, 4), "traffic": None, "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % tc_burst,
+        exec_ratio = (89.7 / 29.24) if args.nnet_precision == "fp16x3" else (29.9 / 29.24)
+        roof_dom = {"kernel": "resnet_gemm_pair_kernel (tcgen05 cta_group::2 dense layers of the cost-to-go ResNet)", "bound": "tensor", "achieved": round(ach, 1),
+                    "peak": tc_sus, "unit": "TFLOP/s", "frac": round(ach / tc_sus, 4), "traffic": None,
+                    "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % tc_burst,
                     "launches": len(gemm_ev), "avg_us": round(t_s / len(gemm_ev) * 1e6, 1), "share_of_timed_region": round(t_s * 1e3 / ms, 4),
-                    "algorithmic_flops": "2*rows*N*K of the unpadded layer (29.24 MFLOP per cube3 state, SURVEY 8d), one product",
-                    "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 2e-5 vs fp64) "
-                            "on tiles padded to 256x64; executed tensor work = %.0f TFLOP/s; ncu: tensor pipe active 77-89%% (profiles/resnet_gemm_r01_ncu.txt); "
-                            "DRAM traffic per K=N=1024 launch at 131072 rows (ncu --set full): 1.03 GB without / 1.60 GB with a residual input vs "
-                            "1.08 / 1.61 GB algorithmic (A hi+lo read, out hi+lo written, residual hi+lo read) -- no re-reads; traffic is null above "
-                            "because the in-loop launches differ in row count"
-                            % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1",
-                               ach * (89.7 / 29.24 if args.nnet_precision == "fp16x3" else 29.9 / 29.24))}
-    if rank == 0:
+                    "algorithmic_flops": "2*rows*N*K of the unpadded layer (%.2f MFLOP per %s state, SURVEY 8d), one product" % (W["mflop"], wl),
+                    "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 3e-5 vs fp64) "
+                            "on padded tiles; executed tensor work ~ %.0f TFLOP/s; traffic is null because the in-loop launches differ in row "
+                            "count (per-layer DRAM bytes at 131072 rows: profiles/)" % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1", ach * exec_ratio)}
+    if rank == 0 and wl == "cube3":
+        alg = 54.0 / 12 + 54 + 1 + 8          # expand + is_solved + hash, unpadded
         n_par = 1 << 21
         g = torch.Generator(device=dev); g.manual_seed(0)
         par = torch.arange(54, dtype=torch.uint8, device=dev).repeat(n_par, 1)
@@ -242,51 +337,66 @@ def run_ours(args):
             if it >= 3:
                 times.append(a.elapsed_time(b))
         t = float(np.mean(times)) * 1e-3
-        ach = ALG_BYTES_PER_CHILD * n_par * 12 / t / 1e9
+        ach = alg * n_par * 12 / t / 1e9
         roof = {"kernel": "expand_kernel<cube3> (expand+is_solved+hash)", "bound": "hbm", "achieved": round(ach, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": NCU_TRAFFIC_BYTES, "peak_source": peak_src,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of this launch shape, profiles/expand_r01_ncu.txt "
-                                  "(algorithmic bytes per launch: %.4g)" % (ALG_BYTES_PER_CHILD * n_par * 12),
+                                  "(algorithmic bytes per launch: %.4g)" % (alg * n_par * 12),
                 "launch": "%d parents -> %d children, outputs 1.7 GB > L2" % (n_par, n_par * 12),
-                "alg_bytes_per_child": ALG_BYTES_PER_CHILD, "children_per_sec": round(n_par * 12 / t, 1)}
+                "alg_bytes_per_child": alg, "children_per_sec": round(n_par * 12 / t, 1)}
         if in_loop:
             tl = float(np.mean([x[0] for x in in_loop])) * 1e-3
             nl = float(np.mean([x[1] for x in in_loop])) * 12
             roof["in_loop"] = {"launches": len(in_loop), "avg_children": nl, "avg_us": round(tl * 1e6, 2),
-                               "achieved": round(ALG_BYTES_PER_CHILD * nl / tl / 1e9, 1),
+                               "achieved": round(alg * nl / tl / 1e9, 1),
                                "note": "A* launches move ~16 MB each: launch-latency bound, not HBM bound"}
         del par, ch
     # ---- reduce over ranks -------------------------------------------------------------------------------------
+    per_rank = [{"rank": rank, "ms": round(ms, 3), "nodes": int(nodes), "heuristic_rows": int(kept), "iterations": int(iters), "solved": int(solved),
+                 "e2e_s": round(e_sec, 4), "e2e_nodes": int(e_nodes)}]
     len_sum = sum(lens)
     if world > 1:
+        bucket = [None] * world
+        dist.all_gather_object(bucket, per_rank[0])
+        per_rank = bucket
         nodes, ms = sharding.reduce_throughput(nodes, ms, dev)            # nodes SUM over ranks, device time MAX over ranks
         e_nodes, e_sec = sharding.reduce_throughput(e_nodes, e_sec, dev)
-        cnt = torch.tensor([launches, solved, len_sum, h2d, d2h], dtype=torch.float64, device=dev)
+        f_nodes, f_sec = sharding.reduce_throughput(f_nodes, f_sec, dev)
+        cnt = torch.tensor([launches, solved, len_sum, h2d, d2h, kept, iters, f_solved, sum(f_lens)], dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        launches, solved, len_sum, h2d, d2h = cnt.tolist()
+        launches, solved, len_sum, h2d, d2h, kept, iters, f_solved, f_len_sum = cnt.tolist()
+    else:
+        f_len_sum = sum(f_lens)
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
             try:
-                cpu = reference_sample(steps=3, warmup=1, use_gpu_heuristic=True)
+                cpu = reference_sample(wl, steps=3, warmup=1, use_gpu_heuristic=True)
             except Exception as e:  # the baseline must never take the bench down
                 cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": "failed: %s" % e}
-        line = {"metric": METRIC, "value": nodes / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        line = {"metric": metric_name(wl), "value": nodes / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "u8 states / u64 hashes / f32 costs; heuristic GEMMs %s" % {
                     "fp32": "fp32 (cuBLAS SGEMM)", "tf32": "tf32 (cuBLAS)", "bf16": "bf16 (cuBLAS)",
                     "fp16x3": "fp16 hi/lo x3 products, fp32 accumulate (tcgen05, fp32-parity mode)",
                     "fp16": "fp16, fp32 accumulate (tcgen05)"}[args.nnet_precision],
-                "data": "synthetic cube3 scrambles (generate_states(n,(0,26)), seed 1234); " + weights_src,
-                "config": {"workload": "cube3 A* weight=0.8 batch_size=20000, scrambles depth<=26 (BASELINE configs[1])",
-                           "step": "one BWAS iteration (pop<=20000, expand 12x, CLOSED, heuristic on survivors, push)",
-                           "instances_per_gpu": len(states), "max_nodes": max_nodes, "parallelism": "instances sharded over %d GPU(s)" % world,
+                "data": "synthetic: " + states_desc + "; " + weights_src,
+                "config": {"workload": W["config"], "states": states_desc,
+                           "step": "one FULL-BATCH BWAS iteration (pop 20000, expand %dx, CLOSED, heuristic on survivors, push); ramp-up "
+                                   "iterations of a new search ride along (time and nodes counted, not steps); the children of a "
+                                   "terminating iteration are not materialised and not counted" % A,
+                           "instances_per_gpu": len(states), "max_nodes": eng.max_nodes, "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world,
                            "l2": "working set (arena+CLOSED+OPEN) >> L2; roofline launches write 1.7 GB each",
-                           "solved_in_timed_region": int(solved), "avg_children_per_step": nodes / args.steps / world,
-                           "avg_heuristic_rows_per_step": kept / args.steps, "mean_solution_len": (len_sum / solved) if solved else None},
-                "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps, "d2h_bytes_per_step": d2h / args.steps,
-                        "note": "BWASGpu.reset(host state)/step()/path_to() wall clock; the search never leaves HBM, only the start "
-                                "state goes in and counters/solution come out"},
+                           "solved_in_timed_region": int(solved), "iterations_in_timed_region": int(iters),
+                           "avg_children_per_step": nodes / args.steps / world, "avg_heuristic_rows_per_step": kept / args.steps / world,
+                           "mean_solution_len": (len_sum / solved) if solved else None, "per_rank": per_rank},
+                "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
+                        "note": "BWASGpu.reset(host state)/step()/path_to() wall clock, same window rule; the search never leaves HBM, only "
+                                "the start state goes in and counters/solution come out"},
+                "full_search": {"value": (f_nodes / f_sec) if f_sec else None, "unit": UNIT, "states": int(args.full_states * world), "solved": int(f_solved),
+                                "nodes_generated": int(f_nodes), "mean_solution_len": (f_len_sum / f_solved) if f_solved else None,
+                                "note": "whole searches to completion right after the window (reference counting: every generated child, "
+                                        "wall clock incl. reset / ramp-up / path); python bench.py --full runs BASELINE configs[1]/[3] this way"},
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof_dom if roof_dom is not None else roof,      # dominant kernel of the step
                 "roofline_gather": roof,                                      # BASELINE.json: "gather-kernel HBM GB/s vs roofline"
@@ -296,30 +406,89 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-# =====================================================================================================
-def reference_sample(steps: int, warmup: int, use_gpu_heuristic: bool = True):
-    """The reference's own C++ BWAS (oracle/_ref/parallel_weighted_astar, compiled from /root/reference/cpp) on
-    the host cores (OpenMP, all threads), heuristic served over its AF_UNIX protocol by a plain PyTorch fp32
-    ResnetModel -- on the GPU when there is one, exactly how the reference's --language cpp path runs."""
+def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
+    """BASELINE configs[1] (1 GPU) / configs[3] (8 GPUs): num_states scrambles PER GPU solved to completion, whole instances
+    handed out by a dynamic queue (a rank that draws easy instances simply takes more of them).  value = sum nodes generated
+    (the reference's counting, scripts/compare_solutions.py:27-28) / wall time of the slowest rank."""
     import torch
-    from oracle import oracle_env as O
+    import torch.distributed as dist
+    from deepcubea_b200 import _lib
+    from deepcubea_b200.search import sharding
+    wl = args.workload
+    W = WORKLOADS[wl]
+    n_total = args.num_states * world
+    states, desc = workload_states(wl, n_total, full=True)
+    q = InstanceQueue(len(states), world)
+    eng.solve(states[0], max_iters=6)                 # warm the kernels / allocator on every rank
+    barrier()
+    t0 = time.perf_counter()
+    mine = []
+    while True:
+        i = q.next()
+        if i is None:
+            break
+        ts = time.perf_counter()
+        try:
+            r = eng.solve(states[i])
+            mine.append((i, len(r.moves) if r.moves is not None else -1, int(r.nodes_generated), time.perf_counter() - ts, int(r.iterations)))
+        except _lib.DcbError as e:
+            mine.append((i, -2, int(eng.nodes_generated), time.perf_counter() - ts, int(eng.iterations)))
+    torch.cuda.synchronize()
+    my_sec = time.perf_counter() - t0
+    barrier()
+    wall = time.perf_counter() - t0
+    rows = [(rank, my_sec, mine)]
+    if world > 1:
+        bucket = [None] * world
+        dist.all_gather_object(bucket, rows[0])
+        rows = bucket
+    if rank == 0:
+        allr = sorted(x for _, _, m in rows for x in m)
+        nodes = sum(x[2] for x in allr)
+        solved = [x for x in allr if x[1] >= 0]
+        max_sec = max(s for _, s, _ in rows)
+        line = {"metric": metric_name(wl), "mode": "full", "value": nodes / max_sec, "unit": UNIT, "n_gpus": world, "higher_is_better": True,
+                "scaling": "weak", "data": "synthetic: " + desc + "; " + weights_src,
+                "config": {"workload": W["config"], "states": desc, "instances": len(allr), "instances_per_gpu": args.num_states,
+                           "queue": "dynamic whole-instance queue (c10d store fetch-add)" if world > 1 else "in order",
+                           "per_rank": [{"rank": r, "seconds": round(s, 3), "instances": len(m), "nodes": sum(x[2] for x in m)} for r, s, m in rows]},
+                "solved": len(solved), "unsolved": len(allr) - len(solved), "nodes_generated": int(nodes), "wall_s": round(wall, 3), "max_rank_s": round(max_sec, 3),
+                "mean_solution_len": float(np.mean([x[1] for x in solved])) if solved else None,
+                "mean_nodes_per_instance": nodes / max(1, len(allr)), "sum_instance_seconds": round(sum(x[3] for x in allr), 3),
+                "balance": {"min_rank_s": round(min(s for _, s, _ in rows), 3), "max_rank_s": round(max_sec, 3)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =====================================================================================================
+def reference_sample(wl: str, steps: int, warmup: int, use_gpu_heuristic: bool = True):
+    """The reference's own C++ BWAS (oracle/_ref/parallel_weighted_astar, compiled from /root/reference/cpp) on the host
+    cores (OpenMP, all threads), heuristic served over its AF_UNIX protocol by a plain PyTorch fp32 ResnetModel -- on the GPU
+    when there is one, exactly how the reference's --language cpp path runs.  Same start states, same step / window / counting
+    rule as run_ours: the window opens when the `warmup`-th full-batch request has been answered and closes when `steps` more
+    have; every child of every request answered inside it counts (the reference materialises all of them)."""
+    import torch
     from oracle.ref_runner import REF_BINARY, HeuristicServer, have_reference_binary
     if not have_reference_binary():
         raise RuntimeError("oracle/_ref/parallel_weighted_astar missing")
     from deepcubea_b200.utils.pytorch_models import ResnetModel
+    W = WORKLOADS[wl]
+    S, A = W["S"], W["A"]
     dev = torch.device("cuda:0") if (use_gpu_heuristic and torch.cuda.is_available()) else torch.device("cpu")
-    model = ResnetModel(54, 6, 5000, 1000, 4, 1, True)
-    if os.path.exists(WEIGHTS):
-        sd = torch.load(WEIGHTS, map_location="cpu")
+    depth = 6 if wl == "cube3" else S
+    model = ResnetModel(S, depth, 5000, 1000, 4, 1, True)
+    wp = weights_path(W["env"])
+    if os.path.exists(wp):
+        sd = torch.load(wp, map_location="cpu")
         model.load_state_dict({k.replace("module.", "", 1): v for k, v in sd.items()})
     else:
         torch.manual_seed(0)
     model.eval().to(dev)
-    env = O.OracleCube3()
     stamps = []
 
     def heur(states: np.ndarray) -> np.ndarray:
-        x = torch.from_numpy(env.nnet_input(states)).to(dev)
+        x = torch.from_numpy((states // 9).astype(np.uint8) if wl == "cube3" else states).to(dev)     # state_to_nnet_input (cube3.py:77-85)
         outs = []
         with torch.no_grad():
             for i in range(0, x.shape[0], 10000):            # --nnet_batch_size 10000 (train.sh)
@@ -328,34 +497,35 @@ def reference_sample(steps: int, warmup: int, use_gpu_heuristic: bool = True):
         stamps.append((time.perf_counter(), states.shape[0]))
         return out
 
-    np.random.seed(1234); random.seed(1234)
-    states, _ = env.generate_states(8, (20, 26))
-    srv = HeuristicServer(54, heur)
-    nodes, t_first, t_last = 0, None, None
+    n_inst = max(8, (steps + warmup) // 2)
+    states, desc = workload_states(wl, n_inst)             # == rank 0's shard of run_ours at N=1
+    srv = HeuristicServer(S, heur)
+    nodes, t_first, t_last, full = 0, None, None, 0
     target = steps + warmup
     try:
         for s in states:
-            stamps.clear()
             # torchrun exports OMP_NUM_THREADS=1; the reference's OpenMP loops get every host thread, as in its own runs
             child_env = dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1))
-            p = subprocess.Popen([REF_BINARY, " ".join(str(int(v)) for v in s), str(WEIGHT), str(BATCH), srv.path, "cube3", "0"],
+            p = subprocess.Popen([REF_BINARY, " ".join(str(int(v)) for v in s), str(W["weight"]), str(BATCH), srv.path, W["env"], "0"],
                                  stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL, env=child_env)
-            # only full-batch iterations count as steps (the first ~6 requests of a search are the ramp-up)
-            full = 0
             seen = 0
-            while p.poll() is None and full < target:
-                time.sleep(0.005)
-                while seen < len(stamps):
+            while full < target:
+                alive = p.poll() is None
+                while seen < len(stamps) and full < target:
                     ts, n = stamps[seen]; seen += 1
-                    if n == BATCH * 12:
+                    if t_first is not None:
+                        nodes += n; t_last = ts
+                    if n == BATCH * A:
                         full += 1
                         if full == warmup:
                             t_first = ts
-                        elif full > warmup and t_first is not None:
-                            nodes += n; t_last = ts
-                    if full >= target:
-                        break
-            p.kill(); p.wait()
+                if not alive and seen >= len(stamps):
+                    break
+                time.sleep(0.002)
+            if p.poll() is None:
+                p.kill()
+            p.wait()
+            stamps.clear()
             if full >= target:
                 break
     finally:
@@ -363,25 +533,28 @@ def reference_sample(steps: int, warmup: int, use_gpu_heuristic: bool = True):
     if not nodes or t_last is None or t_last <= t_first:
         raise RuntimeError("reference sample produced no full-batch iteration")
     return {"value": nodes / (t_last - t_first), "unit": UNIT, "cores": os.cpu_count(), "kind": "reference",
-            "sample": "%d full BWAS iterations (20000 pops, 240000 children each) of oracle/_ref/parallel_weighted_astar, OpenMP on %d "
-                      "host threads, heuristic = PyTorch fp32 ResnetModel on %s over the reference's AF_UNIX protocol"
-                      % (steps, os.cpu_count(), "cuda:0" if dev.type == "cuda" else "cpu")}
+            "sample": "%d full-batch BWAS iterations (20000 pops, %d children each; ramp-up iterations in between counted) of "
+                      "oracle/_ref/parallel_weighted_astar on %s, OpenMP on %d host threads, heuristic = PyTorch fp32 ResnetModel on %s over "
+                      "the reference's AF_UNIX protocol" % (steps, BATCH * A, desc, os.cpu_count(), "cuda:0" if dev.type == "cuda" else "cpu"),
+            "states": desc}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    wl = args.workload
+    W = WORKLOADS[wl]
     try:
-        r = reference_sample(args.steps, max(args.warmup, 1))
+        r = reference_sample(wl, args.steps, max(args.warmup, 1))
     except Exception as e:
         print(json.dumps({"impl": "reference", "unavailable": str(e).replace("\n", " ")[:200]}))
         return
-    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 240000.0 / r["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8 states; f32 costs; heuristic fp32", "data": "synthetic cube3 scrambles (depth 20-26, seed 1234)",
-            "config": {"workload": "cube3 A* weight=0.8 batch_size=20000, scrambles depth<=26 (BASELINE configs[1])",
-                       "step": "one BWAS iteration of the reference C++ program (bounded sample)"},
+    line = {"impl": "reference", "metric": metric_name(wl), "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": BATCH * W["A"] / r["value"] * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u8 states; f32 costs; heuristic fp32", "data": "synthetic: " + r["states"],
+            "config": {"workload": W["config"], "states": r["states"],
+                       "step": "one FULL-BATCH BWAS iteration of the reference C++ program (bounded sample; same states, window and counting rule as the CUDA arm)"},
             "cpu_baseline": r, "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -392,9 +565,14 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", type=str, default="cube3", choices=sorted(WORKLOADS))
     ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp16x3"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"],
-                    help="heuristic arithmetic: fp16x3 = hand-written tcgen05, fp32-parity (max err 2e-5 vs fp64; default); fp32 = cuBLAS SGEMM")
+                    help="heuristic arithmetic: fp16x3 = hand-written tcgen05, fp32-parity (max err 3e-5 vs fp64; default); fp32 = cuBLAS SGEMM")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--max_nodes", type=int, default=1 << 27, help="node arena capacity per GPU (a cube3 search of the reference's test set needs up to 6.1e7)")
+    ap.add_argument("--full_states", type=int, default=2, help="whole searches per GPU run to completion after the window (full_search in the line)")
+    ap.add_argument("--full", action="store_true", help="run --num_states start states per GPU to completion (BASELINE configs[1]/[3]) instead of the window")
+    ap.add_argument("--num_states", type=int, default=1000)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -60,6 +60,9 @@ _SIGS = {
     "dcb_compute_cost": (c_int, [_P, _P, _P, _P, c_float, c_int64, _P, _P]),
     "dcb_reconstruct_path": (c_int, [c_int, _P, c_uint32, c_int32, _P, _P, _P]),
     "dcb_resnet_gemm": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
+    "dcb_resnet_gemm_ex": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32,
+                                   _P, c_int32, c_int32, _P, _P]),
+    "dcb_resnet_gemm_scratch_bytes": (c_int64, []),
     "dcb_onehot_fp16": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "dcb_onehot_fp16_nodes": (c_int, [c_int, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
     "dcb_rowdot": (c_int, [_P, _P, _P, c_float, c_int64, c_int32, c_int32, _P, _P]),

@@ -36,7 +36,8 @@ int cost_device(const float *h, const uint32_t *ids, const uint32_t *node_g, con
 int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const void *w_hi, const void *w_lo, int64_t ldw, const float *bias,
                        float scale, const void *skip_hi, const void *skip_lo, int relu, void *out_hi, void *out_lo, float *out_f32,
                        const float *partial_in, float *partial_out, const float *dot_w, float *dot_partial, int64_t M, int Np, int Kp,
-                       cudaStream_t st);
+                       const int32_t *m_dev, int32_t m_off, int chunk_k, void *scratch, cudaStream_t st);
+int64_t resnet_gemm_scratch_bytes();
 int onehot_device(const uint8_t *x, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
 int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
 int rowdot_device(const void *x_hi, const void *x_lo, const float *w, float bias, int64_t M, int n_valid, int ld, float *out, cudaStream_t st);
@@ -318,19 +319,32 @@ int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_i
 }
 
 // ---- cost-to-go network: tcgen05 dense layers ----------------------------------------------------------------
+int dcb_resnet_gemm_ex(const void *d_a_hi, const void *d_a_lo, int64_t lda, const void *d_w_hi, const void *d_w_lo, int64_t ldw,
+                       const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
+                       void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, const float *d_dot_w,
+                       float *d_dot_partial, int64_t m, int32_t n_padded, int32_t k_padded, const int32_t *d_m_count, int32_t m_offset,
+                       int32_t k_chunk, void *d_scratch, void *stream) {
+  if (m < 0 || n_padded <= 0 || k_padded <= 0 || n_padded % 256 || k_padded % 64 || lda < k_padded || ldw < k_padded || (lda % 8) || (ldw % 8))
+    return DCB_ERR_BAD_ARG;
+  if (m > 0 && (!d_a_hi || !d_w_hi || (!d_partial_out && (!d_bias || (!d_out_hi && !d_dot_w && !d_out_f32))) || (d_dot_w && !d_dot_partial))) return DCB_ERR_BAD_ARG;
+  if (k_chunk < 0 || (k_chunk % 64) || (k_chunk > 0 && k_chunk < k_padded && !d_scratch)) return DCB_ERR_BAD_ARG;
+  if (d_out_lo && !d_out_hi) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_a_hi) || !aligned16(d_a_lo) || !aligned16(d_w_hi) || !aligned16(d_w_lo) || !aligned16(d_skip_hi) || !aligned16(d_skip_lo) ||
+      !aligned16(d_out_hi) || !aligned16(d_out_lo) || !aligned16(d_out_f32) || !aligned16(d_partial_in) || !aligned16(d_partial_out) ||
+      !aligned16(d_scratch))
+    return DCB_ERR_ALIGN;
+  return resnet_gemm_device(d_a_hi, d_a_lo, lda, d_w_hi, d_w_lo, ldw, d_bias, scale, d_skip_hi, d_skip_lo, relu, d_out_hi, d_out_lo, d_out_f32,
+                            d_partial_in, d_partial_out, d_dot_w, d_dot_partial, m, n_padded, k_padded, d_m_count, m_offset, k_chunk, d_scratch,
+                            S(stream));
+}
 int dcb_resnet_gemm(const void *d_a_hi, const void *d_a_lo, int64_t lda, const void *d_w_hi, const void *d_w_lo, int64_t ldw,
                     const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
                     void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, const float *d_dot_w,
                     float *d_dot_partial, int64_t m, int32_t n_padded, int32_t k_padded, void *stream) {
-  if (m < 0 || n_padded <= 0 || k_padded <= 0 || n_padded % 256 || k_padded % 64 || lda < k_padded || ldw < k_padded || (lda % 8) || (ldw % 8))
-    return DCB_ERR_BAD_ARG;
-  if (m > 0 && (!d_a_hi || !d_w_hi || (!d_partial_out && (!d_bias || (!d_out_hi && !d_dot_w))) || (d_dot_w && !d_dot_partial))) return DCB_ERR_BAD_ARG;
-  if (!aligned16(d_a_hi) || !aligned16(d_a_lo) || !aligned16(d_w_hi) || !aligned16(d_w_lo) || !aligned16(d_skip_hi) || !aligned16(d_skip_lo) ||
-      !aligned16(d_out_hi) || !aligned16(d_out_lo) || !aligned16(d_out_f32) || !aligned16(d_partial_in) || !aligned16(d_partial_out))
-    return DCB_ERR_ALIGN;
-  return resnet_gemm_device(d_a_hi, d_a_lo, lda, d_w_hi, d_w_lo, ldw, d_bias, scale, d_skip_hi, d_skip_lo, relu, d_out_hi, d_out_lo, d_out_f32,
-                            d_partial_in, d_partial_out, d_dot_w, d_dot_partial, m, n_padded, k_padded, S(stream));
+  return dcb_resnet_gemm_ex(d_a_hi, d_a_lo, lda, d_w_hi, d_w_lo, ldw, d_bias, scale, d_skip_hi, d_skip_lo, relu, d_out_hi, d_out_lo, d_out_f32,
+                            d_partial_in, d_partial_out, d_dot_w, d_dot_partial, m, n_padded, k_padded, nullptr, 0, 0, nullptr, stream);
 }
+int64_t dcb_resnet_gemm_scratch_bytes(void) { return resnet_gemm_scratch_bytes(); }
 int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int32_t depth, int32_t k_padded, void *d_out, void *stream) {
   if (m < 0 || state_dim <= 0 || depth <= 0 || k_padded < state_dim * depth || k_padded % 64 || (m > 0 && (!d_nnet_in || !d_out))) return DCB_ERR_BAD_ARG;
   if (!aligned16(d_out)) return DCB_ERR_ALIGN;

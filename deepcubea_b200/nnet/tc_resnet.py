@@ -50,7 +50,7 @@ class _Layer:
 class TcResnet:
     """Callable: nnet-input u8 [m, S] on the device -> cost-to-go f32 [m] on the device."""
 
-    def __init__(self, model: nn.Module, device: torch.device, mode: str = "fp16x3", chunk: int = 1 << 16):
+    def __init__(self, model: nn.Module, device: torch.device, mode: str = "fp16x3", chunk: int = 1 << 18):
         assert mode in ("fp16x3", "fp16")
         self.lib = _lib.load()
         self.mode, self.dev, self.chunk = mode, device, chunk
@@ -79,6 +79,7 @@ class TcResnet:
         self.flops_per_row = sum(2 * l.n * l.k for l in self.layers)           # algorithmic (unpadded, one product): 29.24 MFLOP for cube3
         self.gemm_events = None     # when a list: (start_event, end_event, algorithmic_flops) per dcb_resnet_gemm launch (bench.py)
         self.gemm_launches = 0
+        self._scratch = None        # per-CTA fp32 partial sums of the on-chip K chunking (dcb_resnet_gemm_ex)
 
     def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols)
@@ -90,33 +91,37 @@ class TcResnet:
 
     # longest K accumulated in one TMEM accumulator in parity mode (see resnet_kernels.cu).  Measured max |error| of the trained
     # cube3 network vs fp64: 2.0e-5 at 1024, 2.8e-5 at 2048, 4.9e-5 at 5120 (1.2e-4 on the reference's golden states: too close to
-    # the 1e-4 bar).  2048 keeps fc2 (K=5120) to three launches.  $DCB_K_CHUNK overrides for experiments.
+    # the 1e-4 bar).  Longer K (fc2: 5120) is folded ON CHIP in equal chunks of <= K_CHUNK inside one launch
+    # (dcb_resnet_gemm_ex, partial sums through an L2-resident per-CTA scratch).  $DCB_K_CHUNK overrides for experiments.
     K_CHUNK = int(__import__('os').environ.get('DCB_K_CHUNK', 2048))
 
-    def _gemm(self, layer: _Layer, a_hi, a_lo, skip_hi, skip_lo, relu: bool, out_hi, out_lo, m: int, st: int, dot=None) -> None:
+    def _k_chunk(self, layer: _Layer) -> int:
+        if not self.split or layer.kp <= self.K_CHUNK:
+            return 0
+        kb = layer.kp // 64
+        n = -(-layer.kp // self.K_CHUNK)
+        return 64 * (-(-kb // n))
+
+    def _gemm(self, layer: _Layer, a_hi, a_lo, skip_hi, skip_lo, relu: bool, out_hi, out_lo, m: int, st: int, dot=None,
+              m_dev=None, m_off: int = 0) -> None:
         lib = self.lib
         use_lo = a_lo is not None and layer.w_lo is not None
         lda, ldw = a_hi.shape[1], layer.kp
-        chunk = self.K_CHUNK if self.split else layer.kp
-        n_chunks = -(-layer.kp // chunk)
-        part = self._buf32("partial", m, layer.np_) if n_chunks > 1 else None
-        for c in range(n_chunks):
-            k0 = c * chunk
-            kc = min(chunk, layer.kp - k0)
-            last = c == n_chunks - 1
-            self.gemm_launches += 1
-            if self.gemm_events is not None:
-                ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
-            check(lib.dcb_resnet_gemm(a_hi.data_ptr() + 2 * k0, (a_lo.data_ptr() + 2 * k0) if use_lo else None, lda,
-                                      layer.w_hi.data_ptr() + 2 * k0, (layer.w_lo.data_ptr() + 2 * k0) if layer.w_lo is not None else None, ldw,
-                                      ptr(layer.bias), layer.scale, ptr(skip_hi) if last else None, ptr(skip_lo) if last else None,
-                                      1 if relu else 0, ptr(out_hi), ptr(out_lo), None,
-                                      ptr(part) if c > 0 else None, None if last else ptr(part),
-                                      ptr(dot[0]) if (dot is not None and last) else None, ptr(dot[1]) if (dot is not None and last) else None,
-                                      m, layer.np_, kc, st), "dcb_resnet_gemm")
-            if self.gemm_events is not None:
-                ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
-                self.gemm_events.append((ev0, ev1, 2.0 * m * layer.n * min(kc, max(layer.k - k0, 0))))
+        kc = self._k_chunk(layer)
+        if kc and self._scratch is None:
+            self._scratch = torch.empty(int(lib.dcb_resnet_gemm_scratch_bytes()), dtype=torch.uint8, device=self.dev)
+        self.gemm_launches += 1
+        if self.gemm_events is not None:
+            ev0 = torch.cuda.Event(enable_timing=True); ev0.record()
+        check(lib.dcb_resnet_gemm_ex(ptr(a_hi), ptr(a_lo) if use_lo else None, lda,
+                                     ptr(layer.w_hi), ptr(layer.w_lo), ldw,
+                                     ptr(layer.bias), layer.scale, ptr(skip_hi), ptr(skip_lo),
+                                     1 if relu else 0, ptr(out_hi), ptr(out_lo), None, None, None,
+                                     ptr(dot[0]) if dot is not None else None, ptr(dot[1]) if dot is not None else None,
+                                     m, layer.np_, layer.kp, ptr(m_dev), m_off, kc, ptr(self._scratch) if kc else None, st), "dcb_resnet_gemm_ex")
+        if self.gemm_events is not None:
+            ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
+            self.gemm_events.append((ev0, ev1, 2.0 * m * layer.n * layer.k))
 
     def _buf32(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols, 32)
@@ -142,8 +147,10 @@ class TcResnet:
         out = torch.empty(n, dtype=torch.float32, device=self.dev)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         sp = self.split
-        for i0 in range(0, n, self.chunk):
-            m = min(self.chunk, n - i0)
+        n_parts = max(1, -(-n // self.chunk))
+        part = -(-(-(-n // n_parts)) // 256) * 256          # equal parts, whole 256-row CTA-pair tiles
+        for i0 in range(0, n, part):
+            m = min(part, n - i0)
             a0 = self._buf("onehot", m, self.k0)
             if x is not None:
                 check(self.lib.dcb_onehot_fp16(ptr(x[i0:i0 + m]), m, self.state_dim, self.depth, self.k0, ptr(a0), st), "dcb_onehot_fp16")

@@ -158,6 +158,7 @@ class BWASGpu:
                                     ptr(self.cost_tmp), None, 0, None, 1, st), "open_push(root)")
         self.next_slot = 1
         self.nodes_generated = 1 if self.semantics == "cpp" else 0       # :166 vs astar.py:168
+        self.nodes_expanded = 0          # children actually materialised (the terminating iteration's are only counted above)
         self.iterations = 0
         self.done = 0
         self.goal_id = NONE
@@ -210,6 +211,7 @@ class BWASGpu:
                 raise _lib.DcbError("node arena full (%d nodes): raise max_nodes" % self.max_nodes)
             first_id = base_slot * A
             m = n_pop * A
+            self.nodes_expanded += m
             # ---- expand (:217-230): children land directly in the arena ----
             if self.expand_events is not None:
                 ev0 = torch.cuda.Event(enable_timing=True); ev0.record()

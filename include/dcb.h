@@ -214,6 +214,20 @@ int dcb_resnet_gemm(const void *d_a_hi, const void *d_a_lo, int64_t lda, const v
                     const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
                     void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, const float *d_dot_w,
                     float *d_dot_partial, int64_t m, int32_t n_padded, int32_t k_padded, void *stream);
+/* Extended form used by the search loop:
+ *   d_m_count / m_offset : optional DEVICE-side row count -- the rows processed are clamp(*d_m_count - m_offset, 0, m), so that an
+ *                          iteration can be enqueued (or captured in a CUDA graph) before the host knows how many children
+ *                          survived CLOSED; `m` is then the capacity of the row buffers.
+ *   k_chunk / d_scratch  : with 0 < k_chunk < k_padded (multiple of 64) the K sweep is folded ON CHIP in chunks of k_chunk per
+ *                          TMEM accumulator (the tensor core's fp32 accumulation truncates, so one accumulator should not see
+ *                          more than ~2048 K), partial sums passing through d_scratch (dcb_resnet_gemm_scratch_bytes() bytes,
+ *                          16-byte aligned; per-CTA, stays in L2) instead of an [m][n] fp32 matrix in HBM. */
+int dcb_resnet_gemm_ex(const void *d_a_hi, const void *d_a_lo, int64_t lda, const void *d_w_hi, const void *d_w_lo, int64_t ldw,
+                       const float *d_bias, float scale, const void *d_skip_hi, const void *d_skip_lo, int relu, void *d_out_hi,
+                       void *d_out_lo, float *d_out_f32, const float *d_partial_in, float *d_partial_out, const float *d_dot_w,
+                       float *d_dot_partial, int64_t m, int32_t n_padded, int32_t k_padded, const int32_t *d_m_count, int32_t m_offset,
+                       int32_t k_chunk, void *d_scratch, void *stream);
+int64_t dcb_resnet_gemm_scratch_bytes(void);
 /* F.one_hot of the nnet input (pytorch_models.py:49-52) as fp16 [m][k_padded], column = position*depth + value. */
 int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int32_t depth, int32_t k_padded, void *d_out,
                     void *stream);
