@@ -18,11 +18,39 @@ class DcbError(RuntimeError):
     pass
 
 
-class OpenState(ctypes.Structure):
-    """dcb_open_state (include/dcb.h)."""
-    _fields_ = [(n, c_uint32) for n in (
-        "size", "n_popped", "thr_key", "thr_id", "min_key", "goal_id", "goal_key", "done",
-        "overflow", "need", "prefix", "cand_count", "n_holes", "n_surv", "take_all", "n_at_pop")]
+class SearchInst(ctypes.Structure):
+    """dcb_search_inst == dcb_open_state (include/dcb.h): one problem instance's record, 128 bytes."""
+    _fields_ = ([(n, c_uint32) for n in ("open_size", "n_popped", "n_expand", "min_key", "goal_id", "goal_key", "done", "n_goals",
+                                         "next_slot", "base_slot", "iterations", "tile_off")] +
+                [("nodes_generated", ctypes.c_uint64), ("nodes_expanded", ctypes.c_uint64)] +
+                [(n, c_uint32) for n in ("thr_key", "thr_id", "need", "prefix", "cand_count", "n_holes", "n_surv", "take_all", "n_at_pop",
+                                         "n_take", "resting", "overflow")] + [("reserved", c_uint32 * 4)])
+
+    @property
+    def size(self) -> int:          # OPEN entries (the stand-alone queue's name for it)
+        return self.open_size
+
+
+OpenState = SearchInst
+INST_WORDS = ctypes.sizeof(SearchInst) // 4
+
+
+class StepPlan(ctypes.Structure):
+    """dcb_step_plan (include/dcb.h), 64 bytes."""
+    _fields_ = ([(n, c_uint32) for n in ("n_tiles", "n_parents", "n_kept", "n_ambiguous", "closed_entries", "n_running", "error", "reserved0")] +
+                [("total_kept", ctypes.c_uint64), ("total_expanded", ctypes.c_uint64), ("reserved1", ctypes.c_uint64 * 2)])
+
+
+PLAN_WORDS = ctypes.sizeof(StepPlan) // 4
+
+
+class SearchCtx(ctypes.Structure):
+    """dcb_search_ctx (include/dcb.h): geometry + device buffers of one engine."""
+    _fields_ = ([(n, c_int32) for n in ("env", "n_inst", "batch", "semantics")] +
+                [("slots_per_inst", c_uint32), ("open_per_inst", c_uint32), ("closed_capacity", c_int64)] +
+                [(n, c_void_p) for n in ("d_arena", "d_node_g", "d_node_solved", "d_slot_parent", "d_closed", "d_open_key", "d_open_id", "d_inst",
+                                         "d_plan", "d_weights", "d_popped_ids", "d_tiles", "d_hash", "d_kept_ids", "d_pop_scratch",
+                                         "d_closed_scratch")])
 
 
 _lib = None
@@ -48,6 +76,7 @@ _SIGS = {
     "dcb_is_solved_host": (c_int, [c_int, _P, c_int64, _P, c_int]),
     "dcb_closed_bytes": (c_int64, [c_int64]),
     "dcb_closed_clear": (c_int, [_P, c_int64, _P]),
+    "dcb_closed_scratch_bytes": (c_int64, [c_int64]),
     "dcb_closed_insert": (c_int, [c_int, _P, c_int64, _P, _P, _P, _P, c_uint32, c_int64, _P, _P, _P, _P]),
     "dcb_closed_rehash": (c_int, [_P, c_int64, _P, c_int64, _P]),
     "dcb_open_clear": (c_int, [_P, _P]),
@@ -59,12 +88,20 @@ _SIGS = {
     "dcb_gather_nnet_input": (c_int, [c_int, _P, _P, c_int64, _P, _P]),
     "dcb_compute_cost": (c_int, [_P, _P, _P, _P, c_float, c_int64, _P, _P]),
     "dcb_reconstruct_path": (c_int, [c_int, _P, c_uint32, c_int32, _P, _P, _P]),
+    "dcb_search_pop_scratch_bytes": (c_int64, [c_int32, c_int64, c_int32]),
+    "dcb_search_reset": (c_int, [_P, _P, _P]),
+    "dcb_search_pop": (c_int, [_P, c_int, _P]),
+    "dcb_search_expand": (c_int, [_P, _P]),
+    "dcb_search_closed": (c_int, [_P, _P]),
+    "dcb_search_push": (c_int, [_P, _P, _P, c_int32, c_float, _P]),
+    "dcb_search_path": (c_int, [_P, c_uint32, c_int32, _P, _P, _P]),
     "dcb_resnet_gemm": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32, _P]),
     "dcb_resnet_gemm_ex": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_float, _P, _P, c_int, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_int32,
                                    _P, c_int32, c_int32, _P, _P]),
     "dcb_resnet_gemm_scratch_bytes": (c_int64, []),
     "dcb_onehot_fp16": (c_int, [_P, c_int64, c_int32, c_int32, c_int32, _P, _P]),
     "dcb_onehot_fp16_nodes": (c_int, [c_int, _P, _P, c_int64, c_int32, c_int32, _P, _P]),
+    "dcb_onehot_fp16_nodes_ex": (c_int, [c_int, _P, _P, c_int64, c_int32, c_int32, _P, _P, c_int32, _P]),
     "dcb_rowdot": (c_int, [_P, _P, _P, c_float, c_int64, c_int32, c_int32, _P, _P]),
 }
 

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcb_b200.so")
-SOURCES = ["api.cu", "expand_kernels.cu", "closed_table.cu", "open_set.cu", "node_ops.cu", "resnet_kernels.cu", "lightsout_kernels.cu"]
+SOURCES = ["api.cu", "expand_kernels.cu", "closed_table.cu", "open_set.cu", "node_ops.cu", "search_step.cu", "resnet_kernels.cu", "lightsout_kernels.cu"]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -18,15 +18,24 @@ int dcb_check_launch() { return dcb_record_cuda(cudaGetLastError()); }
 
 int closed_clear_device(void *tbl, int64_t cap, cudaStream_t st);
 int closed_insert_device(int env, void *tbl, int64_t cap, const uint8_t *arena, const uint64_t *hash, const uint32_t *g,
-                         const uint8_t *valid, uint32_t first_id, int64_t m, uint32_t *slot, uint8_t *keep,
+                         const uint8_t *valid, uint32_t first_id, int64_t m, void *scratch, uint8_t *keep,
                          uint32_t *num_entries, cudaStream_t st);
+int64_t closed_scratch_bytes(int64_t m);
 int closed_rehash_device(const void *old_tbl, int64_t old_cap, void *new_tbl, int64_t new_cap, cudaStream_t st);
-int open_clear_device(void *state, cudaStream_t st);
+int open_clear_device(void *state, int n_inst, cudaStream_t st);
 int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
                      uint32_t first_id, const uint8_t *keep, int64_t m, cudaStream_t st);
-int64_t open_scratch_bytes(int64_t capacity, int64_t batch);
-int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, int32_t batch, int stop_at_goal,
-                    const uint8_t *node_solved, uint32_t *popped_ids, void *scratch, cudaStream_t st);
+int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst);
+int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
+                    int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
+                    int64_t popped_stride, void *scratch, cudaStream_t st);
+int search_reset_device(const dcb_search_ctx &c, const uint8_t *roots, cudaStream_t st);
+int search_pop_device(const dcb_search_ctx &c, int include_solved, cudaStream_t st);
+int search_expand_device(const dcb_search_ctx &c, cudaStream_t st);
+int search_closed_device(const dcb_search_ctx &c, cudaStream_t st);
+int search_push_device(const dcb_search_ctx &c, const float *h, const float *dot_partial, int n_parts, float dot_bias, cudaStream_t st);
+int search_path_device(const dcb_search_ctx &c, uint32_t node_id, int32_t max_len, uint8_t *moves, int32_t *len, cudaStream_t st);
+int64_t search_pop_scratch_bytes(int32_t n_inst, int64_t open_per_inst, int32_t batch);
 int child_meta_device(const uint32_t *parent_ids, int64_t n_parents, int A, uint32_t first_id, uint32_t *node_g,
                       uint32_t *slot_parent, cudaStream_t st);
 int compact_kept_device(const uint8_t *keep, uint32_t first_id, int64_t m, uint32_t *out_ids, uint32_t *counter, cudaStream_t st);
@@ -39,7 +48,8 @@ int resnet_gemm_device(const void *a_hi, const void *a_lo, int64_t lda, const vo
                        const int32_t *m_dev, int32_t m_off, int chunk_k, void *scratch, cudaStream_t st);
 int64_t resnet_gemm_scratch_bytes();
 int onehot_device(const uint8_t *x, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
-int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st);
+int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, const int32_t *m_dev,
+                         int32_t m_off, cudaStream_t st);
 int rowdot_device(const void *x_hi, const void *x_lo, const float *w, float bias, int64_t M, int n_valid, int ld, float *out, cudaStream_t st);
 int path_device(const uint32_t *slot_parent, uint32_t goal_id, int A, int32_t max_len, uint8_t *moves, int32_t *len, cudaStream_t st);
 }  // namespace dcb
@@ -254,14 +264,16 @@ int dcb_closed_clear(void *d_table, int64_t capacity, void *stream) {
   if (!aligned16(d_table)) return DCB_ERR_ALIGN;
   return closed_clear_device(d_table, capacity, S(stream));
 }
+int64_t dcb_closed_scratch_bytes(int64_t m) { return m >= 0 ? closed_scratch_bytes(m) : DCB_ERR_BAD_ARG; }
 int dcb_closed_insert(int env, void *d_table, int64_t capacity, const uint8_t *d_arena, const uint64_t *d_hash,
-                      const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id, int64_t m, uint32_t *d_slot,
+                      const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id, int64_t m, void *d_scratch,
                       uint8_t *d_keep, uint32_t *d_num_entries, void *stream) {
   if (!env_ok(env)) return DCB_ERR_BAD_ENV;
-  if (m < 0 || !pow2(capacity) || capacity > (int64_t(1) << 32) || (m > 0 && (!d_table || !d_arena || !d_hash || !d_g || !d_slot || !d_keep)))
+  // slot indices are 32-bit with 0xffffffff = "no slot": the table stops at 2^31 slots (32 GB)
+  if (m < 0 || !pow2(capacity) || capacity > (int64_t(1) << 31) || (m > 0 && (!d_table || !d_arena || !d_hash || !d_g || !d_scratch || !d_keep)))
     return DCB_ERR_BAD_ARG;
-  if (!aligned16(d_table) || (reinterpret_cast<uintptr_t>(d_arena) & 3u)) return DCB_ERR_ALIGN;
-  return closed_insert_device(env, d_table, capacity, d_arena, d_hash, d_g, d_valid, first_id, m, d_slot, d_keep, d_num_entries,
+  if (!aligned16(d_table) || !aligned16(d_scratch) || (reinterpret_cast<uintptr_t>(d_arena) & 3u)) return DCB_ERR_ALIGN;
+  return closed_insert_device(env, d_table, capacity, d_arena, d_hash, d_g, d_valid, first_id, m, d_scratch, d_keep, d_num_entries,
                               S(stream));
 }
 int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int64_t new_capacity, void *stream) {
@@ -272,7 +284,7 @@ int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int6
 // ---- OPEN ------------------------------------------------------------------------------------------------
 int dcb_open_clear(dcb_open_state *d_state, void *stream) {
   if (!d_state) return DCB_ERR_BAD_ARG;
-  return open_clear_device(d_state, S(stream));
+  return open_clear_device(d_state, 1, S(stream));
 }
 int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, const float *d_cost,
                   const uint32_t *d_ids, uint32_t first_id, const uint8_t *d_keep, int64_t m, void *stream) {
@@ -280,14 +292,15 @@ int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int6
   return open_push_device(d_state, d_key, d_id, capacity, d_cost, d_ids, first_id, d_keep, m, S(stream));
 }
 int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch) {
-  return (capacity > 0 && batch > 0) ? open_scratch_bytes(capacity, batch) : DCB_ERR_BAD_ARG;
+  return (capacity > 0 && batch > 0) ? open_scratch_bytes(capacity, batch, 1) : DCB_ERR_BAD_ARG;
 }
 int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, int32_t batch, int stop_at_goal,
                  const uint8_t *d_node_solved, uint32_t *d_popped_ids, void *d_scratch, void *stream) {
   if (!d_state || !d_key || !d_id || !d_popped_ids || !d_scratch || batch <= 0 || capacity <= 0) return DCB_ERR_BAD_ARG;
   if (stop_at_goal && !d_node_solved) return DCB_ERR_BAD_ARG;
   if (!aligned16(d_scratch)) return DCB_ERR_ALIGN;
-  return open_pop_device(d_state, d_key, d_id, capacity, batch, stop_at_goal, d_node_solved, d_popped_ids, d_scratch, S(stream));
+  return open_pop_device(d_state, d_key, d_id, capacity, 1, batch, -1, stop_at_goal, 0, 0, d_node_solved, nullptr, d_popped_ids, batch, d_scratch,
+                         S(stream));
 }
 
 // ---- node bookkeeping --------------------------------------------------------------------------------------
@@ -316,6 +329,56 @@ int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_i
   if (!env_ok(env)) return DCB_ERR_BAD_ENV;
   if (!d_slot_parent || !d_moves || !d_len || max_len <= 0) return DCB_ERR_BAD_ARG;
   return path_device(d_slot_parent, goal_id, kNumMoves[env], max_len, d_moves, d_len, S(stream));
+}
+
+// ---- device-driven search iteration ---------------------------------------------------------------------------
+static int ctx_ok(const dcb_search_ctx *c) {
+  if (!c) return DCB_ERR_BAD_ARG;
+  if (!env_ok(c->env)) return DCB_ERR_BAD_ENV;
+  const int64_t a = kNumMoves[c->env];
+  if (c->n_inst <= 0 || c->n_inst > 65535 || c->batch <= 0 || (c->semantics != 0 && c->semantics != 1)) return DCB_ERR_BAD_ARG;
+  if (c->slots_per_inst < 64 || c->slots_per_inst % 32 || (int64_t)c->n_inst * c->slots_per_inst * a >= (int64_t(1) << 32)) return DCB_ERR_BAD_ARG;
+  if (c->open_per_inst == 0 || !pow2(c->closed_capacity) || c->closed_capacity > (int64_t(1) << 31)) return DCB_ERR_BAD_ARG;
+  if (!c->d_arena || !c->d_node_g || !c->d_node_solved || !c->d_slot_parent || !c->d_closed || !c->d_open_key || !c->d_open_id || !c->d_inst ||
+      !c->d_plan || !c->d_weights || !c->d_popped_ids || !c->d_tiles || !c->d_hash || !c->d_kept_ids || !c->d_pop_scratch || !c->d_closed_scratch)
+    return DCB_ERR_BAD_ARG;
+  if (!aligned16(c->d_arena) || !aligned16(c->d_closed) || !aligned16(c->d_hash) || !aligned16(c->d_tiles) || !aligned16(c->d_pop_scratch) ||
+      !aligned16(c->d_closed_scratch) || !aligned16(c->d_inst) || !aligned16(c->d_plan) || (reinterpret_cast<uintptr_t>(c->d_node_solved) & 3u))
+    return DCB_ERR_ALIGN;
+  return DCB_OK;
+}
+int64_t dcb_search_pop_scratch_bytes(int32_t n_inst, int64_t open_per_inst, int32_t batch) {
+  return (n_inst > 0 && open_per_inst > 0 && batch > 0) ? search_pop_scratch_bytes(n_inst, open_per_inst, batch) : DCB_ERR_BAD_ARG;
+}
+int dcb_search_reset(const dcb_search_ctx *ctx, const uint8_t *d_roots, void *stream) {
+  const int rc = ctx_ok(ctx);
+  if (rc) return rc;
+  if (!d_roots) return DCB_ERR_BAD_ARG;
+  return search_reset_device(*ctx, d_roots, S(stream));
+}
+int dcb_search_pop(const dcb_search_ctx *ctx, int include_solved, void *stream) {
+  const int rc = ctx_ok(ctx);
+  return rc ? rc : search_pop_device(*ctx, include_solved, S(stream));
+}
+int dcb_search_expand(const dcb_search_ctx *ctx, void *stream) {
+  const int rc = ctx_ok(ctx);
+  return rc ? rc : search_expand_device(*ctx, S(stream));
+}
+int dcb_search_closed(const dcb_search_ctx *ctx, void *stream) {
+  const int rc = ctx_ok(ctx);
+  return rc ? rc : search_closed_device(*ctx, S(stream));
+}
+int dcb_search_push(const dcb_search_ctx *ctx, const float *d_h, const float *d_dot_partial, int32_t n_parts, float dot_bias, void *stream) {
+  const int rc = ctx_ok(ctx);
+  if (rc) return rc;
+  if ((!d_h && !d_dot_partial) || (d_dot_partial && n_parts <= 0)) return DCB_ERR_BAD_ARG;
+  return search_push_device(*ctx, d_h, d_dot_partial, n_parts, dot_bias, S(stream));
+}
+int dcb_search_path(const dcb_search_ctx *ctx, uint32_t node_id, int32_t max_len, uint8_t *d_moves, int32_t *d_len, void *stream) {
+  const int rc = ctx_ok(ctx);
+  if (rc) return rc;
+  if (!d_moves || !d_len || max_len <= 0) return DCB_ERR_BAD_ARG;
+  return search_path_device(*ctx, node_id, max_len, d_moves, d_len, S(stream));
 }
 
 // ---- cost-to-go network: tcgen05 dense layers ----------------------------------------------------------------
@@ -356,7 +419,15 @@ int dcb_onehot_fp16_nodes(int env, const uint8_t *d_arena, const uint32_t *d_ids
   const int s = kStateBytes[env];
   if (m < 0 || depth <= 0 || k_padded < s * depth || k_padded % 64 || (m > 0 && (!d_arena || !d_ids || !d_out))) return DCB_ERR_BAD_ARG;
   if (!aligned16(d_out)) return DCB_ERR_ALIGN;
-  return onehot_gather_device(env, d_arena, d_ids, m, s, depth, k_padded, d_out, S(stream));
+  return onehot_gather_device(env, d_arena, d_ids, m, s, depth, k_padded, d_out, nullptr, 0, S(stream));
+}
+int dcb_onehot_fp16_nodes_ex(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, int32_t depth, int32_t k_padded, void *d_out,
+                             const int32_t *d_m_count, int32_t m_offset, void *stream) {
+  if (!env_ok(env)) return DCB_ERR_BAD_ENV;
+  const int s = kStateBytes[env];
+  if (m < 0 || depth <= 0 || k_padded < s * depth || k_padded % 64 || (m > 0 && (!d_arena || !d_ids || !d_out))) return DCB_ERR_BAD_ARG;
+  if (!aligned16(d_out)) return DCB_ERR_ALIGN;
+  return onehot_gather_device(env, d_arena, d_ids, m, s, depth, k_padded, d_out, d_m_count, m_offset, S(stream));
 }
 int dcb_rowdot(const void *d_x_hi, const void *d_x_lo, const float *d_w, float bias, int64_t m, int32_t n_valid, int32_t ld, float *d_out,
                void *stream) {

@@ -84,10 +84,23 @@ __device__ __forceinline__ void team_sync(int split, int team) {
 // would land in the same banks (32-way conflict).  The lanes' slots are then PAD bytes apart in shared memory (2320-byte
 // stride: eight lanes' 16-byte stores tile all 32 banks) and every lane ships its own record with its own bulk store -- the
 // tile is no longer one contiguous block, but 2304-byte bulk copies are still large enough for the TMA engine.
-template <int ENV, bool INDEXED, int TEAMS, int SPLIT, int PAD = 0>
+//
+// PLANNED (the search loop, dcb_search_expand): the work is the iteration's TILE LIST in device memory (include/dcb.h) instead
+// of a contiguous parent range -- tile t = {src, dst_slot, count, inst}: parents ids[src + lane], children to arena slots
+// dst_slot + lane, solved flags to node_solved[(dst_slot + lane) * A ...], hashes to hash[(t * 32 + lane) * A ...]; the tile
+// count is read from the plan, so the launch needs no host-side size.  The lane that owns a parent also writes its children's
+// depth (parent depth + 1, parallel_weighted_astar.cpp:219) and the slot's parent link (Node::parent, :221).
+struct ExpandPlan {
+  const uint4 *tiles;
+  const dcb_step_plan *plan;
+  uint32_t *node_g;
+  uint32_t *slot_parent;
+};
+
+template <int ENV, bool INDEXED, int TEAMS, int SPLIT, int PAD = 0, bool PLANNED = false>
 __global__ void __launch_bounds__(TEAMS * SPLIT * 32)
 expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids, int64_t n,
-              uint8_t *__restrict__ children, uint8_t *__restrict__ solved, uint64_t *__restrict__ hash) {
+              uint8_t *__restrict__ children, uint8_t *__restrict__ solved, uint64_t *__restrict__ hash, ExpandPlan ep) {
   using Sh = ExpandShape<ENV>;
   static_assert(Sh::A % (SPLIT * Sh::GROUP) == 0, "moves must split into whole packing groups");
   static_assert(PAD == 0 || (SPLIT == 1 && PAD % 16 == 0 && Sh::REC_BYTES % 16 == 0), "per-lane bulk stores need 16-byte records");
@@ -99,24 +112,38 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
   uint32_t *lane_rec = reinterpret_cast<uint32_t *>(tile_smem + lane * (Sh::REC_BYTES + PAD));
   const bool issuer = member == 0 && lane == 0;
 
-  const int64_t n_tiles = (n + 31) >> 5;
+  const int64_t n_tiles = PLANNED ? (int64_t)ep.plan->n_tiles : ((n + 31) >> 5);
   const int64_t tile_stride = (int64_t)gridDim.x * TEAMS;
   // software pipeline: the parent words of the next tile are requested before this tile is computed
   uint32_t raw_next[LoadShape<Sh::S>::NRAW];
   uint64_t off_next = 0;
+  uint4 desc_next = make_uint4(0, 0, 0, 0);
   int64_t tile = (int64_t)blockIdx.x * TEAMS + team;
   auto issue_loads = [&](int64_t t) {
-    const int64_t p = t * 32 + lane;
-    if (t < n_tiles && p < n) {
-      const uint64_t node = INDEXED ? (uint64_t)ids[p] : (uint64_t)p;
-      off_next = node * Sh::S;
-      load_raw<Sh::S>(src, off_next, raw_next);
+    if constexpr (PLANNED) {
+      if (t < n_tiles) {
+        desc_next = ep.tiles[t];
+        if ((uint32_t)lane < desc_next.z) {
+          off_next = (uint64_t)ids[desc_next.x + lane] * Sh::S;
+          load_raw<Sh::S>(src, off_next, raw_next);
+        }
+      }
+    } else {
+      const int64_t p = t * 32 + lane;
+      if (t < n_tiles && p < n) {
+        const uint64_t node = INDEXED ? (uint64_t)ids[p] : (uint64_t)p;
+        off_next = node * Sh::S;
+        load_raw<Sh::S>(src, off_next, raw_next);
+      }
     }
   };
   issue_loads(tile);
   for (; tile < n_tiles; tile += tile_stride) {
-    const int64_t p = tile * 32 + lane;
-    const bool valid = p < n;
+    const uint4 desc = desc_next;
+    // p: index of this lane's parent in the output numbering (children / solved at p * A ...); hp: in the hash numbering
+    const int64_t p = PLANNED ? (int64_t)desc.y + lane : tile * 32 + lane;
+    const int64_t hp = tile * 32 + lane;
+    const bool valid = PLANNED ? ((uint32_t)lane < desc.z) : (p < n);
     uint32_t raw[LoadShape<Sh::S>::NRAW];
 #pragma unroll
     for (int k = 0; k < LoadShape<Sh::S>::NRAW; k++) raw[k] = raw_next[k];
@@ -133,8 +160,18 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
       align_state<Sh::S, Sh::W>(raw, (uint32_t)(off & 3), w);
       SmemSink<ENV> sink;
       sink.rec = lane_rec;
-      sink.hash_out = hash ? hash + p * Sh::A : nullptr;
+      sink.hash_out = hash ? hash + hp * Sh::A : nullptr;
       sink.solved_out = solved ? reinterpret_cast<uint16_t *>(solved + p * Sh::A) : nullptr;
+      if constexpr (PLANNED) {
+        if (member == 0) {                                   // Node{depth, parent} of the children (:219-226)
+          const uint32_t pid = (uint32_t)(off / Sh::S);
+          const uint32_t gc = ep.node_g[pid] + 1;
+          uint32_t *gdst = ep.node_g + p * Sh::A;
+#pragma unroll
+          for (int a = 0; a < Sh::A; a++) gdst[a] = gc;
+          ep.slot_parent[p] = pid;
+        }
+      }
       constexpr int PER = Sh::A / SPLIT;
       if constexpr (SPLIT == 1) expand_parent<ENV, SmemSink<ENV>, 0, Sh::A>(w, sink);
       else if (member == 0) expand_parent<ENV, SmemSink<ENV>, 0, PER>(w, sink);
@@ -149,10 +186,10 @@ expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids,
       continue;
     }
     team_sync(SPLIT, team);
-    const int64_t rem = n - tile * 32;
+    const int64_t rem = PLANNED ? (int64_t)desc.z : n - tile * 32;
     const uint32_t bytes = (uint32_t)((rem < 32 ? rem : 32) * Sh::REC_BYTES);
     const uint32_t bulk = bytes & ~15u;
-    uint8_t *gdst = children + tile * (int64_t)kTileBytes;
+    uint8_t *gdst = PLANNED ? children + (int64_t)desc.y * Sh::REC_BYTES : children + tile * (int64_t)kTileBytes;
     if (issuer && bulk) {
       bulk_store_s2g(gdst, tile_smem, bulk);
       bulk_commit();
@@ -269,7 +306,31 @@ static int launch_expand_cfg(const uint8_t *src, const uint32_t *ids, int64_t n,
   int64_t blocks = (n_tiles + TEAMS - 1) / TEAMS;
   const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
   if (blocks > cap) blocks = cap;
-  kern<<<(unsigned)blocks, threads, smem, st>>>(src, ids, n, children, solved, hash);
+  kern<<<(unsigned)blocks, threads, smem, st>>>(src, ids, n, children, solved, hash, ExpandPlan{});
+  return dcb_check_launch();
+}
+
+// the search loop's form: work = the iteration's tile list, sizes in device memory
+template <int ENV, int TEAMS, int SPLIT, int PAD = 0>
+static int launch_expand_planned_cfg(const uint8_t *arena, const uint32_t *ids, int64_t max_tiles, const ExpandPlan &ep, uint8_t *node_solved,
+                                     uint64_t *hash, cudaStream_t st) {
+  using Sh = ExpandShape<ENV>;
+  constexpr int smem = TEAMS * 32 * (Sh::REC_BYTES + PAD);
+  constexpr int threads = TEAMS * SPLIT * 32;
+  static bool configured = false;
+  static int blocks_per_sm = 1;
+  auto kern = expand_kernel<ENV, true, TEAMS, SPLIT, PAD, true>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) return dcb_cuda_fail();
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, threads, smem) != cudaSuccess) return dcb_cuda_fail();
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    configured = true;
+  }
+  int64_t blocks = (max_tiles + TEAMS - 1) / TEAMS;
+  const int64_t cap = (int64_t)num_sms() * blocks_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  kern<<<(unsigned)blocks, threads, smem, st>>>(arena, ids, 0, const_cast<uint8_t *>(arena), node_solved, hash, ep);
   return dcb_check_launch();
 }
 
@@ -327,6 +388,25 @@ static int dispatch_expand(int env, const uint8_t *src, const uint32_t *ids, int
     case 4: return launch_expand<4, INDEXED>(src, ids, n, children, solved, hash, st);
     case 5: return lightsout_expand_device(src, ids, n, children, solved, hash, st);
     case 6: return launch_expand<6, INDEXED>(src, ids, n, children, solved, hash, st);
+  }
+  return DCB_ERR_BAD_ENV;
+}
+
+int expand_planned_device(int env, uint8_t *arena, const uint32_t *ids, int64_t max_tiles, const uint32_t *tiles, const dcb_step_plan *plan,
+                          uint8_t *node_solved, uint64_t *hash, uint32_t *node_g, uint32_t *slot_parent, cudaStream_t st) {
+  const ExpandPlan ep{reinterpret_cast<const uint4 *>(tiles), plan, node_g, slot_parent};
+  // A* launches are small (625 tiles at B = 20000): one tile per team, and for cube3 two warps share a tile's 12 moves so the
+  // tile is computed in half the time (DCB_EXPAND_CFG=4x1 selects the streaming shape)
+  switch (env) {
+    case 0:
+      if (cube3_cfg() == 1) return launch_expand_planned_cfg<0, 4, 1>(arena, ids, max_tiles, ep, node_solved, hash, st);
+      return launch_expand_planned_cfg<0, 2, 2>(arena, ids, max_tiles, ep, node_solved, hash, st);
+    case 1: return launch_expand_planned_cfg<1, 4, 1>(arena, ids, max_tiles, ep, node_solved, hash, st);
+    case 2: return launch_expand_planned_cfg<2, 4, 1>(arena, ids, max_tiles, ep, node_solved, hash, st);
+    case 3: return launch_expand_planned_cfg<3, 4, 1>(arena, ids, max_tiles, ep, node_solved, hash, st);
+    case 4: return launch_expand_planned_cfg<4, 4, 1>(arena, ids, max_tiles, ep, node_solved, hash, st);
+    case 5: return lightsout_expand_planned_device(arena, ids, max_tiles, tiles, plan, node_solved, hash, node_g, slot_parent, st);
+    case 6: return launch_expand_planned_cfg<6, 3, 1, 16>(arena, ids, max_tiles, ep, node_solved, hash, st);
   }
   return DCB_ERR_BAD_ENV;
 }

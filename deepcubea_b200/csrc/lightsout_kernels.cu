@@ -32,20 +32,37 @@ __device__ __forceinline__ uint32_t word_at(const uint64_t *cbits, int byte_in_t
   return lo_spread4((uint32_t)x);
 }
 
-template <bool INDEXED>
+// PLANNED (dcb_search_expand): a 32-parent tile of the iteration's tile list = two 16-parent CTA tiles; parents ids[src + k],
+// children to arena slots dst_slot + k (dst_slot is a multiple of 16), hashes in tile numbering, depth / parent link written here.
+template <bool INDEXED, bool PLANNED>
 __global__ void __launch_bounds__(256)
 lightsout_expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restrict__ ids, int64_t n, uint8_t *__restrict__ children,
-                        uint8_t *__restrict__ solved, uint64_t *__restrict__ hash) {
+                        uint8_t *__restrict__ solved, uint64_t *__restrict__ hash, const uint4 *__restrict__ tiles,
+                        const dcb_step_plan *__restrict__ plan, uint32_t *__restrict__ node_g, uint32_t *__restrict__ slot_parent) {
   __shared__ uint64_t pbits[TILE_P];
   __shared__ uint64_t cbits[TILE_C + 1];
-  const int64_t n_tiles = (n + TILE_P - 1) / TILE_P;
+  const int64_t n_tiles = PLANNED ? 2 * (int64_t)plan->n_tiles : (n + TILE_P - 1) / TILE_P;
   for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t p0 = tile * TILE_P;
-    const int np = (int)((n - p0) < TILE_P ? (n - p0) : TILE_P);
+    int64_t p0 = tile * TILE_P;        // first parent in the output numbering (children / solved)
+    int64_t h0 = p0;                   // ... in the hash numbering
+    int64_t s0 = p0;                   // ... in ids[]
+    int np;
+    if constexpr (PLANNED) {
+      const uint4 d = tiles[tile >> 1];
+      const int half = (int)(tile & 1) * TILE_P;
+      np = (int)d.z - half;
+      np = np < 0 ? 0 : (np > TILE_P ? TILE_P : np);
+      p0 = (int64_t)d.y + half;
+      h0 = (tile >> 1) * 32 + half;
+      s0 = (int64_t)d.x + half;
+    } else {
+      np = (int)((n - p0) < TILE_P ? (n - p0) : TILE_P);
+    }
     __syncthreads();                                       // previous tile fully written out
     if (threadIdx.x < np) {
-      const uint64_t node = INDEXED ? (uint64_t)ids[p0 + threadIdx.x] : (uint64_t)(p0 + threadIdx.x);
+      const uint64_t node = INDEXED ? (uint64_t)ids[s0 + threadIdx.x] : (uint64_t)(p0 + threadIdx.x);
       pbits[threadIdx.x] = load_state_bits(src, node * S);
+      if constexpr (PLANNED) slot_parent[p0 + threadIdx.x] = (uint32_t)node;
     }
     if (threadIdx.x == 0) cbits[np * A] = 0;               // pad entry read by the last straddling word
     __syncthreads();
@@ -55,8 +72,9 @@ lightsout_expand_kernel(const uint8_t *__restrict__ src, const uint32_t *__restr
       cbits[c] = b;
       uint32_t w[W];
       lo_words_from_bits<S, W>(b, w);
-      if (hash) hash[(p0 + p) * A + m] = state_hash<W>(w);
+      if (hash) hash[(h0 + p) * A + m] = state_hash<W>(w);
       if (solved) solved[(p0 + p) * A + m] = (b == 0) ? 1 : 0;
+      if constexpr (PLANNED) node_g[(p0 + p) * A + m] = node_g[ids[s0 + p]] + 1;
     }
     __syncthreads();
     uint8_t *out = children + p0 * (int64_t)(A * S);        // 16-byte aligned: 16 parents x 2401 bytes
@@ -80,8 +98,18 @@ int lightsout_expand_device(const uint8_t *src, const uint32_t *ids, int64_t n, 
   if (n == 0) return DCB_OK;
   int64_t blocks = (n + TILE_P - 1) / TILE_P;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  if (ids) lightsout_expand_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(src, ids, n, children, solved, hash);
-  else lightsout_expand_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(src, nullptr, n, children, solved, hash);
+  if (ids) lightsout_expand_kernel<true, false><<<(unsigned)blocks, 256, 0, st>>>(src, ids, n, children, solved, hash, nullptr, nullptr, nullptr, nullptr);
+  else lightsout_expand_kernel<false, false><<<(unsigned)blocks, 256, 0, st>>>(src, nullptr, n, children, solved, hash, nullptr, nullptr, nullptr, nullptr);
+  return dcb_check_launch();
+}
+
+int lightsout_expand_planned_device(uint8_t *arena, const uint32_t *ids, int64_t max_tiles, const uint32_t *tiles, const dcb_step_plan *plan,
+                                    uint8_t *node_solved, uint64_t *hash, uint32_t *node_g, uint32_t *slot_parent, cudaStream_t st) {
+  int64_t blocks = 2 * max_tiles;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  lightsout_expand_kernel<true, true><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, 0, arena, node_solved, hash, reinterpret_cast<const uint4 *>(tiles),
+                                                                        plan, node_g, slot_parent);
   return dcb_check_launch();
 }
 }  // namespace dcb

@@ -3,7 +3,7 @@
 // Replaces std::priority_queue<Node*,std::vector<Node*>,compareNodeCost> open, the one-at-a-time pop
 // loop (with its `break` at the first solved node) and the push loop of
 // cpp/parallel_weighted_astar.cpp:141, 177-208, 309-319; heapq open_set / pop_from_open / push_to_open of
-// search_methods/astar.py:53, 64-76.
+// search_methods/astar.py:53, 64-76, and the per-instance loop of astar.py:93-96 (every unsolved instance pops per step).
 //
 // Entries are (key = cost's float bits, id) in flat unsorted arrays.  Costs are >= 0 so unsigned key order
 // is cost order; ties break towards the smaller node id, which makes every (key,id) distinct and the popped
@@ -14,9 +14,13 @@
 //      the select on their remaining 40 bits -> exact threshold T;
 //   3. one partition pass removes everything <= T, back-filling the holes from the array tail;
 //   4. the popped list is sorted (bucketed rank sort) into cost order (the reference's pop order, so child node ids are
-//      deterministic) and the goal / termination rule of :190-208 is applied on the device; entries behind
-//      the first solved pop go back to OPEN, exactly like the reference's `break`.
+//      deterministic) and the goal / termination rule of :190-208 (or astar.py:73) is applied on the device; in the C++
+//      semantics entries behind the first solved pop go back to OPEN, exactly like the reference's `break`.
 // HBM traffic per pop: 4 passes x 4 B per open entry; per push: 8 B per entry.
+//
+// SEGMENTED: every kernel runs with gridDim.y = number of problem instances.  Instance i owns the OPEN segment
+// key/id[i * seg_cap ...], the record states[i] and its own slice of the scratch buffer, so many A* instances are popped by
+// the same launches as one.  Nothing here needs the host: counts stay in the per-instance records.
 #include <cuda_runtime.h>
 #include "dcb_internal.h"
 
@@ -26,11 +30,7 @@ namespace {
 constexpr int kBins = 4096;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 
-struct OpenState {           // mirrors dcb_open_state (include/dcb.h)
-  uint32_t size, n_popped, thr_key, thr_id, min_key, goal_id, goal_key, done;
-  uint32_t overflow, need, prefix, cand_count, n_holes, n_surv, take_all, n_at_pop;
-};
-static_assert(sizeof(OpenState) == sizeof(dcb_open_state), "state layout");
+typedef dcb_search_inst OpenState;      // per-instance record (include/dcb.h); dcb_open_state is the same type
 
 __device__ __forceinline__ uint32_t warp_agg_inc(uint32_t *ctr, bool pred) {
   // one atomic per warp; returns this lane's slot (undefined if !pred)
@@ -48,7 +48,7 @@ __global__ void open_clear_kernel(OpenState *s) {
     OpenState z = {};
     z.goal_id = kNone;
     z.goal_key = kNone;
-    *s = z;
+    s[blockIdx.x] = z;
   }
 }
 
@@ -57,7 +57,7 @@ open_push_kernel(OpenState *s, uint32_t *key, uint32_t *id, uint32_t capacity, c
                  uint32_t first_id, const uint8_t *keep, int64_t m) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const bool want = i < m && (!keep || keep[i]);
-  const uint32_t pos = warp_agg_inc(&s->size, want);
+  const uint32_t pos = warp_agg_inc(&s->open_size, want);
   if (want) {
     if (pos < capacity) {
       key[pos] = __float_as_uint(cost[i]);
@@ -77,22 +77,74 @@ struct SortScratch {                     // lives in the pop scratch buffer
   uint32_t cursor[kSortBins];
 };
 
-__global__ void open_pop_begin_kernel(OpenState *s, uint32_t *hist, int32_t batch, SortScratch *ss) {
-  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) hist[i] = 0;
-  for (int i = threadIdx.x; i <= kSortBins; i += blockDim.x) ss->counts[i] = 0;
-  for (int i = threadIdx.x; i < kSortBins; i += blockDim.x) ss->cursor[i] = 0;
-  if (threadIdx.x == 0) { ss->min64 = ~0ull; ss->max64 = 0ull; }
+// where instance blockIdx.y keeps its things
+struct Seg {
+  OpenState *states;
+  uint32_t *key, *id;
+  uint64_t seg_cap;              // OPEN entries per instance
+  uint8_t *scratch;
+  uint64_t scratch_stride;       // bytes of pop scratch per instance
+  uint32_t *popped_ids;          // [n_inst][popped_stride]
+  uint32_t popped_stride;
+  int32_t batch;
+};
+struct Carve {                   // one instance's view
+  OpenState *s;
+  uint32_t *key, *id;
+  uint32_t *hist;
+  SortScratch *ss;
+  unsigned long long *cand, *popped, *sorted, *tmp;
+  uint32_t *holes, *surv, *popped_ids;
+};
+__host__ __device__ inline uint64_t sort_scratch_bytes() { return (sizeof(SortScratch) + 15) / 16 * 16; }
+// per-instance scratch layout (bytes): hist 2*4096*4 | sort scratch | cand 8*cap | popped 8*batch | sorted 8*batch | tmp 8*batch | holes 4*batch | surv 4*batch
+__host__ __device__ inline uint64_t pop_scratch_stride(uint64_t seg_cap, uint64_t batch) {
+  return (2 * kBins * 4 + sort_scratch_bytes() + 8 * seg_cap + 32 * batch + 255) / 256 * 256;
+}
+__device__ __forceinline__ Carve carve(const Seg &g) {
+  const uint32_t inst = blockIdx.y;
+  Carve c;
+  c.s = g.states + inst;
+  c.key = g.key + inst * g.seg_cap;
+  c.id = g.id + inst * g.seg_cap;
+  uint8_t *p = g.scratch + inst * g.scratch_stride;
+  c.hist = reinterpret_cast<uint32_t *>(p); p += 2 * kBins * 4;
+  c.ss = reinterpret_cast<SortScratch *>(p); p += sort_scratch_bytes();
+  c.cand = reinterpret_cast<unsigned long long *>(p); p += 8 * g.seg_cap;
+  c.popped = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
+  c.sorted = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
+  c.tmp = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
+  c.holes = reinterpret_cast<uint32_t *>(p); p += 4 * (uint64_t)g.batch;
+  c.surv = reinterpret_cast<uint32_t *>(p);
+  c.popped_ids = g.popped_ids + (uint64_t)inst * g.popped_stride;
+  return c;
+}
+
+// mode: 0 = C++ semantics, 1 = Python semantics (instances that found their goal rest unless include_solved), -1 = stand-alone
+// queue (dcb_open_pop: C++ goal rule when asked, never rests)
+__global__ void open_pop_begin_kernel(Seg g, int mode, int include_solved) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
+  for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) c.hist[i] = 0;
+  for (int i = threadIdx.x; i <= kSortBins; i += blockDim.x) c.ss->counts[i] = 0;
+  for (int i = threadIdx.x; i < kSortBins; i += blockDim.x) c.ss->cursor[i] = 0;
+  if (threadIdx.x == 0) { c.ss->min64 = ~0ull; c.ss->max64 = 0ull; }
   if (threadIdx.x == 0) {
-    const uint32_t n = s->size;
-    const uint32_t b = n < (uint32_t)batch ? n : (uint32_t)batch;
+    // an instance rests once it is done (C++: the loop test at :169; Python: astar.py:263-265 skips instances with a goal node)
+    const bool rest = mode >= 0 && s->done != 0 && !(mode == 1 && include_solved && s->done == 1);
+    const uint32_t n = s->open_size;
+    const uint32_t b = rest ? 0u : (n < (uint32_t)g.batch ? n : (uint32_t)g.batch);
+    s->resting = rest ? 1u : 0u;
     s->n_at_pop = n;
+    s->n_take = b;
     s->need = b;                 // select the b smallest
-    s->take_all = (b == n);
+    s->take_all = (b == n || b == 0);
     s->prefix = 0;
     s->cand_count = 0;
     s->n_holes = 0;
     s->n_surv = 0;
     s->n_popped = 0;
+    s->n_expand = 0;
     s->thr_key = kNone;
     s->thr_id = kNone;
   }
@@ -101,33 +153,38 @@ __global__ void open_pop_begin_kernel(OpenState *s, uint32_t *hist, int32_t batc
 // LEVEL 0: bucket = key >> 20 over all entries.  LEVEL 1: bucket = (key >> 8) & 0xFFF over entries whose
 // top 12 bits equal the level-0 boundary bucket.
 template <int LEVEL>
-__global__ void __launch_bounds__(512) open_hist_kernel(const OpenState *s, const uint32_t *__restrict__ key, uint32_t *hist) {
+__global__ void __launch_bounds__(512) open_hist_kernel(Seg g) {
+  const Carve c = carve(g);
+  const OpenState *s = c.s;
   if (s->take_all) return;
   __shared__ uint32_t sh[kBins];
   for (int i = threadIdx.x; i < kBins; i += blockDim.x) sh[i] = 0;
   __syncthreads();
   const uint32_t n = s->n_at_pop, prefix = s->prefix;
+  const uint32_t *__restrict__ key = c.key;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const uint32_t k = key[i];
     if (LEVEL == 0) atomicAdd(&sh[k >> 20], 1u);
     else if ((k >> 20) == prefix) atomicAdd(&sh[(k >> 8) & 0xFFF], 1u);
   }
   __syncthreads();
-  uint32_t *h = hist + LEVEL * kBins;
+  uint32_t *h = c.hist + LEVEL * kBins;
   for (int i = threadIdx.x; i < kBins; i += blockDim.x)
     if (sh[i]) atomicAdd(&h[i], sh[i]);
 }
 
 // Single block: find the bucket in which the cumulative count reaches `need`.
-template <int LEVEL> __global__ void __launch_bounds__(1024) open_scan_kernel(OpenState *s, const uint32_t *hist) {
+template <int LEVEL> __global__ void __launch_bounds__(1024) open_scan_kernel(Seg g) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
   if (s->take_all) return;
   __shared__ uint32_t part[1024];
-  const uint32_t *h = hist + LEVEL * kBins;
+  const uint32_t *h = c.hist + LEVEL * kBins;
   const int t = threadIdx.x;
   const uint32_t need = s->need, prefix_in = s->prefix;   // read before anyone writes them back
-  uint32_t c[4], sum = 0;
+  uint32_t cnt[4], sum = 0;
 #pragma unroll
-  for (int q = 0; q < 4; q++) { c[q] = h[4 * t + q]; sum += c[q]; }
+  for (int q = 0; q < 4; q++) { cnt[q] = h[4 * t + q]; sum += cnt[q]; }
   part[t] = sum;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {   // Hillis-Steele inclusive scan
@@ -141,36 +198,41 @@ template <int LEVEL> __global__ void __launch_bounds__(1024) open_scan_kernel(Op
     uint32_t below = excl;
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      if (below + c[q] >= need) {
+      if (below + cnt[q] >= need) {
         s->prefix = (LEVEL == 0) ? (uint32_t)(4 * t + q) : ((prefix_in << 12) | (uint32_t)(4 * t + q));
         s->need = need - below;                // still to take from inside this bucket
         break;
       }
-      below += c[q];
+      below += cnt[q];
     }
   }
 }
 
 // Collect the composite keys of the boundary bucket (top 24 key bits == prefix).
-__global__ void __launch_bounds__(512)
-open_collect_kernel(OpenState *s, const uint32_t *__restrict__ key, const uint32_t *__restrict__ id, unsigned long long *cand) {
+__global__ void __launch_bounds__(512) open_collect_kernel(Seg g) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
   if (s->take_all) return;
   const uint32_t n = s->n_at_pop, prefix = s->prefix;
+  const uint32_t *__restrict__ key = c.key, *__restrict__ id = c.id;
   for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + threadIdx.x;
     const bool hit = i < n && (key[i] >> 8) == prefix;
     const uint32_t pos = warp_agg_inc(&s->cand_count, hit);
-    if (hit) cand[pos] = ((unsigned long long)key[i] << 32) | id[i];
+    if (hit) c.cand[pos] = ((unsigned long long)key[i] << 32) | id[i];
   }
 }
 
 // Single block: the `need`-th smallest of the candidates, by 8-bit radix passes over their low 40 bits.
-__global__ void __launch_bounds__(1024) open_select_finish_kernel(OpenState *s, const unsigned long long *cand) {
+__global__ void __launch_bounds__(1024) open_select_finish_kernel(Seg g) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
   if (s->take_all) return;
   __shared__ uint32_t hist[256];
   __shared__ unsigned long long sel_prefix;
   __shared__ uint32_t sel_need;
-  const uint32_t c = s->cand_count;
+  const uint32_t nc = s->cand_count;
+  const unsigned long long *cand = c.cand;
   if (threadIdx.x == 0) { sel_prefix = (unsigned long long)s->prefix; sel_need = s->need; }   // 24 bits known
   __syncthreads();
   for (int pass = 0; pass < 5; pass++) {
@@ -178,7 +240,7 @@ __global__ void __launch_bounds__(1024) open_select_finish_kernel(OpenState *s, 
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
     const unsigned long long pre = sel_prefix;
-    for (uint32_t i = threadIdx.x; i < c; i += blockDim.x) {
+    for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
       const unsigned long long v = cand[i];
       if ((v >> (shift + 8)) == pre) atomicAdd(&hist[(uint32_t)(v >> shift) & 0xFF], 1u);
     }
@@ -202,13 +264,15 @@ __global__ void __launch_bounds__(1024) open_select_finish_kernel(OpenState *s, 
 }
 
 // Partition: pop everything <= threshold; remember holes in the kept prefix and survivors in the tail.
-__global__ void __launch_bounds__(512)
-open_partition_kernel(OpenState *s, const uint32_t *__restrict__ key, const uint32_t *__restrict__ id, int32_t batch,
-                      unsigned long long *popped, uint32_t *holes, uint32_t *surv, SortScratch *ss) {
+__global__ void __launch_bounds__(512) open_partition_kernel(Seg g) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
+  const uint32_t b = s->n_take;
+  if (b == 0) return;
   const uint32_t n = s->n_at_pop;
-  const uint32_t b = n < (uint32_t)batch ? n : (uint32_t)batch;
   const uint32_t new_size = n - b;
   const uint32_t tk = s->thr_key, ti = s->thr_id;
+  const uint32_t *__restrict__ key = c.key, *__restrict__ id = c.id;
   for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + threadIdx.x;
     bool pop = false, hole = false, sv = false;
@@ -225,22 +289,23 @@ open_partition_kernel(OpenState *s, const uint32_t *__restrict__ key, const uint
     const uint32_t pp = warp_agg_inc(&s->n_popped, pop);
     if (pop) {
       const unsigned long long v = ((unsigned long long)k << 32) | d;
-      popped[pp] = v;
-      atomicMin(&ss->min64, v);
-      atomicMax(&ss->max64, v);
+      c.popped[pp] = v;
+      atomicMin(&c.ss->min64, v);
+      atomicMax(&c.ss->max64, v);
     }
     const uint32_t hp = warp_agg_inc(&s->n_holes, hole);
-    if (hole) holes[hp] = i;
+    if (hole) c.holes[hp] = i;
     const uint32_t sp = warp_agg_inc(&s->n_surv, sv);
-    if (sv) surv[sp] = i;
+    if (sv) c.surv[sp] = i;
   }
 }
 
-__global__ void __launch_bounds__(256) open_fill_holes_kernel(const OpenState *s, uint32_t *key, uint32_t *id, const uint32_t *holes, const uint32_t *surv) {
-  const uint32_t cnt = s->n_holes;   // == n_surv
+__global__ void __launch_bounds__(256) open_fill_holes_kernel(Seg g) {
+  const Carve c = carve(g);
+  const uint32_t cnt = c.s->n_holes;   // == n_surv
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
-    key[holes[j]] = key[surv[j]];
-    id[holes[j]] = id[surv[j]];
+    c.key[c.holes[j]] = c.key[c.surv[j]];
+    c.id[c.holes[j]] = c.id[c.surv[j]];
   }
 }
 
@@ -252,21 +317,25 @@ __device__ __forceinline__ uint32_t sort_bucket(unsigned long long v, unsigned l
   const uint32_t b = (uint32_t)x;
   return b < (uint32_t)kSortBins ? b : (uint32_t)(kSortBins - 1);
 }
-__device__ __forceinline__ double sort_scale(const OpenState *, const SortScratch *ss) {
+__device__ __forceinline__ double sort_scale(const SortScratch *ss) {
   const unsigned long long hi = ss->max64, lo = ss->min64;
   return (hi >= lo) ? (double)kSortBins / ((double)(hi - lo) + 1.0) : 0.0;
 }
-__global__ void __launch_bounds__(256) open_sort_count_kernel(const OpenState *s, const unsigned long long *__restrict__ popped, SortScratch *ss) {
-  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b) return;
-  atomicAdd(&ss->counts[sort_bucket(popped[i], ss->min64, sort_scale(s, ss))], 1u);
+__global__ void __launch_bounds__(256) open_sort_count_kernel(Seg g) {
+  const Carve c = carve(g);
+  const uint32_t b = c.s->n_popped;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x)
+    atomicAdd(&c.ss->counts[sort_bucket(c.popped[i], c.ss->min64, sort_scale(c.ss))], 1u);
 }
-__global__ void __launch_bounds__(1024) open_sort_scan_kernel(SortScratch *ss) {      // exclusive scan of kSortBins counts
+__global__ void __launch_bounds__(1024) open_sort_scan_kernel(Seg g) {      // exclusive scan of kSortBins counts
+  const Carve c = carve(g);
+  if (c.s->n_popped == 0) return;
+  SortScratch *ss = c.ss;
   __shared__ uint32_t part[1024];
   const int t = threadIdx.x;
-  uint32_t c[4], sum = 0;
+  uint32_t cnt[4], sum = 0;
 #pragma unroll
-  for (int q = 0; q < 4; q++) { c[q] = ss->counts[4 * t + q]; sum += c[q]; }
+  for (int q = 0; q < 4; q++) { cnt[q] = ss->counts[4 * t + q]; sum += cnt[q]; }
   part[t] = sum;
   __syncthreads();
   for (int off = 1; off < 1024; off <<= 1) {
@@ -277,79 +346,109 @@ __global__ void __launch_bounds__(1024) open_sort_scan_kernel(SortScratch *ss) {
   }
   uint32_t run = part[t] - sum;
 #pragma unroll
-  for (int q = 0; q < 4; q++) { ss->counts[4 * t + q] = run; run += c[q]; }
+  for (int q = 0; q < 4; q++) { ss->counts[4 * t + q] = run; run += cnt[q]; }
   if (t == 1023) ss->counts[kSortBins] = run;
 }
-__global__ void __launch_bounds__(256)
-open_sort_scatter_kernel(const OpenState *s, const unsigned long long *__restrict__ popped, SortScratch *ss, unsigned long long *tmp) {
-  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b) return;
-  const unsigned long long v = popped[i];
-  const uint32_t k = sort_bucket(v, ss->min64, sort_scale(s, ss));
-  tmp[ss->counts[k] + atomicAdd(&ss->cursor[k], 1u)] = v;
+__global__ void __launch_bounds__(256) open_sort_scatter_kernel(Seg g) {
+  const Carve c = carve(g);
+  const uint32_t b = c.s->n_popped;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
+    const unsigned long long v = c.popped[i];
+    const uint32_t k = sort_bucket(v, c.ss->min64, sort_scale(c.ss));
+    c.tmp[c.ss->counts[k] + atomicAdd(&c.ss->cursor[k], 1u)] = v;
+  }
 }
-__global__ void __launch_bounds__(256)
-open_sort_rank_kernel(const OpenState *s, const SortScratch *ss, const unsigned long long *__restrict__ tmp, unsigned long long *sorted) {
-  const uint32_t b = s->n_popped, i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= b) return;
-  const unsigned long long v = tmp[i];
-  const uint32_t k = sort_bucket(v, ss->min64, sort_scale(s, ss));
-  const uint32_t lo = ss->counts[k], hi = ss->counts[k + 1];
-  uint32_t rank = lo;
-  for (uint32_t j = lo; j < hi; j++) rank += tmp[j] < v;
-  sorted[rank] = v;
+__global__ void __launch_bounds__(256) open_sort_rank_kernel(Seg g) {
+  const Carve c = carve(g);
+  const uint32_t b = c.s->n_popped;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
+    const unsigned long long v = c.tmp[i];
+    const uint32_t k = sort_bucket(v, c.ss->min64, sort_scale(c.ss));
+    const uint32_t lo = c.ss->counts[k], hi = c.ss->counts[k + 1];
+    uint32_t rank = lo;
+    for (uint32_t j = lo; j < hi; j++) rank += c.tmp[j] < v;
+    c.sorted[rank] = v;
+  }
 }
 
-// Single block: goal bookkeeping + termination (parallel_weighted_astar.cpp:186-208) and un-popping the
-// entries behind the first solved pop.
+// Single block per instance: goal bookkeeping + termination and, in the C++ semantics, un-popping the entries behind the
+// first solved pop.
+//   mode 0, stop_at_goal: parallel_weighted_astar.cpp:186-208.   mode 0, !stop_at_goal: plain pop (no goal logic).
+//   mode 1: search_methods/astar.py:69-76 -- every popped node stands; solved pops are goal nodes (:73); the caller's loop ends
+//           once an instance has one (:421); the answer is the goal node of smallest path cost, first one on ties (:327-333).
 __global__ void __launch_bounds__(1024)
-open_finalize_kernel(OpenState *s, uint32_t *key, uint32_t *id, int32_t batch, int stop_at_goal,
-                     const uint8_t *__restrict__ node_solved, const unsigned long long *__restrict__ sorted, uint32_t *popped_ids) {
+open_finalize_kernel(Seg g, int mode, int stop_at_goal, int num_moves, const uint8_t *__restrict__ node_solved,
+                     const uint32_t *__restrict__ node_g) {
+  const Carve c = carve(g);
+  OpenState *s = c.s;
   __shared__ uint32_t first_solved;
+  __shared__ unsigned long long best_goal;       // python: (g << 32) | position in pop order
+  __shared__ uint32_t goals_here;
+  if (s->resting) return;
   const uint32_t b = s->n_popped;
   const uint32_t n = s->n_at_pop;
   const uint32_t new_size = n - b;
-  if (threadIdx.x == 0) first_solved = kNone;
+  const unsigned long long *__restrict__ sorted = c.sorted;
+  if (threadIdx.x == 0) { first_solved = kNone; best_goal = ~0ull; goals_here = 0; }
   __syncthreads();
-  if (stop_at_goal && node_solved) {
+  if (mode <= 0 && stop_at_goal && node_solved) {
     uint32_t best = kNone;
     for (uint32_t j = threadIdx.x; j < b; j += blockDim.x)
       if (node_solved[(uint32_t)sorted[j]]) { best = j; break; }   // j ascending per thread
     if (best != kNone) atomicMin(&first_solved, best);
+  } else if (mode == 1) {
+    for (uint32_t j = threadIdx.x; j < b; j += blockDim.x) {
+      const uint32_t nid = (uint32_t)sorted[j];
+      if (node_solved[nid]) {
+        atomicAdd(&goals_here, 1u);
+        atomicMin(&best_goal, ((unsigned long long)node_g[nid] << 32) | j);
+      }
+    }
   }
   __syncthreads();
   const uint32_t fs = first_solved;
   const uint32_t m = (fs != kNone) ? fs + 1 : b;                    // pops that stand
   for (uint32_t j = threadIdx.x; j < b; j += blockDim.x) {
     const unsigned long long v = sorted[j];
-    if (j < m) popped_ids[j] = (uint32_t)v;
+    if (j < m) c.popped_ids[j] = (uint32_t)v;
     else {                                                         // back to OPEN
-      key[new_size + (j - m)] = (uint32_t)(v >> 32);
-      id[new_size + (j - m)] = (uint32_t)v;
+      c.key[new_size + (j - m)] = (uint32_t)(v >> 32);
+      c.id[new_size + (j - m)] = (uint32_t)v;
     }
   }
   if (threadIdx.x == 0) {
-    const bool goal_prev = s->goal_id != kNone;
     uint32_t done = s->done;
-    if (fs != kNone) {
-      const uint32_t gk = (uint32_t)(sorted[fs] >> 32), gi = (uint32_t)sorted[fs];
-      if (batch == 1) { s->goal_id = gi; s->goal_key = gk; done = 1; }            // :191-193
-      else if (!goal_prev || s->goal_key > gk) { s->goal_id = gi; s->goal_key = gk; }  // :195-199
-    }
     const uint32_t min_key = b ? (uint32_t)(sorted[0] >> 32) : kNone;
-    if (goal_prev && b && min_key >= s->goal_key) done = 1;                         // :205-208
+    if (mode <= 0) {
+      const bool goal_prev = s->goal_id != kNone;
+      if (fs != kNone) {
+        const uint32_t gk = (uint32_t)(sorted[fs] >> 32), gi = (uint32_t)sorted[fs];
+        if (g.batch == 1) { s->goal_id = gi; s->goal_key = gk; done = 1; }            // :191-193
+        else if (!goal_prev || s->goal_key > gk) { s->goal_id = gi; s->goal_key = gk; }  // :195-199
+      }
+      if (stop_at_goal && goal_prev && b && min_key >= s->goal_key) done = 1;         // :205-208
+    } else if (goals_here) {
+      const uint32_t gg = (uint32_t)(best_goal >> 32), pos = (uint32_t)best_goal;
+      if (s->goal_id == kNone || gg < s->goal_key) { s->goal_id = (uint32_t)sorted[pos]; s->goal_key = gg; }
+      s->n_goals += goals_here;
+      done = 1;
+    }
     if (b == 0) done = 2;                                                            // OPEN exhausted
     s->min_key = min_key;
     s->done = done;
     s->n_popped = m;
-    s->size = new_size + (b - m);
+    s->open_size = new_size + (b - m);
+    s->iterations += 1;
+    s->nodes_generated += (uint64_t)m * (uint64_t)num_moves;     // :266 -- counted on the terminating iteration too; astar.py:168
+    // C++: the terminating iteration's children are never needed (the loop test :169 fails first); Python expands every pop
+    s->n_expand = (mode <= 0 && done) ? 0u : m;
   }
 }
 }  // namespace
 
 // ---- host launchers --------------------------------------------------------------------------------
-int open_clear_device(void *state, cudaStream_t st) {
-  open_clear_kernel<<<1, 32, 0, st>>>(reinterpret_cast<OpenState *>(state));
+int open_clear_device(void *state, int n_inst, cudaStream_t st) {
+  open_clear_kernel<<<(unsigned)n_inst, 32, 0, st>>>(reinterpret_cast<OpenState *>(state));
   return dcb_check_launch();
 }
 
@@ -361,39 +460,45 @@ int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity,
   return dcb_check_launch();
 }
 
-// scratch layout (bytes): hist 2*4096*4 | sort scratch | cand 8*cap | popped 8*batch | sorted 8*batch | tmp 8*batch | holes 4*batch | surv 4*batch
-int64_t open_scratch_bytes(int64_t capacity, int64_t batch) {
-  return 2 * kBins * 4 + (int64_t)((sizeof(SortScratch) + 15) / 16 * 16) + 8 * capacity + 32 * batch + 256;
+int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst) {
+  return (int64_t)pop_scratch_stride((uint64_t)capacity, (uint64_t)batch) * n_inst + 256;
 }
 
-int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, int32_t batch, int stop_at_goal,
-                    const uint8_t *node_solved, uint32_t *popped_ids, void *scratch, cudaStream_t st) {
-  OpenState *s = reinterpret_cast<OpenState *>(state);
-  uint8_t *p = reinterpret_cast<uint8_t *>(scratch);
-  uint32_t *hist = reinterpret_cast<uint32_t *>(p); p += 2 * kBins * 4;
-  SortScratch *ss = reinterpret_cast<SortScratch *>(p); p += (sizeof(SortScratch) + 15) / 16 * 16;
-  unsigned long long *cand = reinterpret_cast<unsigned long long *>(p); p += 8 * capacity;
-  unsigned long long *popped = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
-  unsigned long long *sorted = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
-  unsigned long long *tmp = reinterpret_cast<unsigned long long *>(p); p += 8 * (int64_t)batch;
-  uint32_t *holes = reinterpret_cast<uint32_t *>(p); p += 4 * (int64_t)batch;
-  uint32_t *surv = reinterpret_cast<uint32_t *>(p);
-  const int full_blocks = 148 * 4;   // grid-stride passes over the whole array
-  open_pop_begin_kernel<<<1, 1024, 0, st>>>(s, hist, batch, ss);
-  open_hist_kernel<0><<<full_blocks, 512, 0, st>>>(s, key, hist);
-  open_scan_kernel<0><<<1, 1024, 0, st>>>(s, hist);
-  open_hist_kernel<1><<<full_blocks, 512, 0, st>>>(s, key, hist);
-  open_scan_kernel<1><<<1, 1024, 0, st>>>(s, hist);
-  open_collect_kernel<<<full_blocks, 512, 0, st>>>(s, key, id, cand);
-  open_select_finish_kernel<<<1, 1024, 0, st>>>(s, cand);
-  open_partition_kernel<<<full_blocks, 512, 0, st>>>(s, key, id, batch, popped, holes, surv, ss);
-  open_fill_holes_kernel<<<(batch + 255) / 256, 256, 0, st>>>(s, key, id, holes, surv);
-  const unsigned sort_blocks = (unsigned)((batch + 255) / 256);
-  open_sort_count_kernel<<<sort_blocks, 256, 0, st>>>(s, popped, ss);
-  open_sort_scan_kernel<<<1, 1024, 0, st>>>(ss);
-  open_sort_scatter_kernel<<<sort_blocks, 256, 0, st>>>(s, popped, ss, tmp);
-  open_sort_rank_kernel<<<sort_blocks, 256, 0, st>>>(s, ss, tmp, sorted);
-  open_finalize_kernel<<<1, 1024, 0, st>>>(s, key, id, batch, stop_at_goal, node_solved, sorted, popped_ids);
+// Pop for n_inst instances at once.  seg_cap = OPEN entries per instance, popped ids of instance i at popped_ids + i*popped_stride.
+int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
+                    int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
+                    int64_t popped_stride, void *scratch, cudaStream_t st) {
+  Seg g;
+  g.states = reinterpret_cast<OpenState *>(state);
+  g.key = key; g.id = id;
+  g.seg_cap = (uint64_t)seg_cap;
+  g.scratch = reinterpret_cast<uint8_t *>(scratch);
+  g.scratch_stride = pop_scratch_stride((uint64_t)seg_cap, (uint64_t)batch);
+  g.popped_ids = popped_ids;
+  g.popped_stride = (uint32_t)popped_stride;
+  g.batch = batch;
+  // grid-stride passes over a whole segment: all SMs for one instance, fewer blocks each as the instance count grows
+  int full_blocks = (148 * 4 + n_inst - 1) / n_inst;
+  const int64_t seg_blocks = (seg_cap + 511) / 512;
+  if (full_blocks > seg_blocks) full_blocks = (int)seg_blocks;
+  if (full_blocks < 1) full_blocks = 1;
+  int batch_blocks = (batch + 255) / 256;
+  if (batch_blocks > full_blocks * 2) batch_blocks = full_blocks * 2;
+  const dim3 one(1, n_inst), full(full_blocks, n_inst), bat(batch_blocks, n_inst);
+  open_pop_begin_kernel<<<one, 1024, 0, st>>>(g, mode, include_solved);
+  open_hist_kernel<0><<<full, 512, 0, st>>>(g);
+  open_scan_kernel<0><<<one, 1024, 0, st>>>(g);
+  open_hist_kernel<1><<<full, 512, 0, st>>>(g);
+  open_scan_kernel<1><<<one, 1024, 0, st>>>(g);
+  open_collect_kernel<<<full, 512, 0, st>>>(g);
+  open_select_finish_kernel<<<one, 1024, 0, st>>>(g);
+  open_partition_kernel<<<full, 512, 0, st>>>(g);
+  open_fill_holes_kernel<<<bat, 256, 0, st>>>(g);
+  open_sort_count_kernel<<<bat, 256, 0, st>>>(g);
+  open_sort_scan_kernel<<<one, 1024, 0, st>>>(g);
+  open_sort_scatter_kernel<<<bat, 256, 0, st>>>(g);
+  open_sort_rank_kernel<<<bat, 256, 0, st>>>(g);
+  open_finalize_kernel<<<one, 1024, 0, st>>>(g, mode, stop_at_goal, num_moves, node_solved, node_g);
   return dcb_check_launch();
 }
 

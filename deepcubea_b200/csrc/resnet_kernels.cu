@@ -544,7 +544,11 @@ __global__ void __launch_bounds__(256) onehot_kernel(const uint8_t *__restrict__
 // state_to_nnet_input (cube3.py:77-85: sticker / 9 -> colour; cube4: sticker / 16) and F.one_hot in one pass, no intermediate u8 matrix
 template <int DIV>
 __global__ void __launch_bounds__(256) onehot_gather_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ ids, int64_t M, int S,
-                                                            int depth, int Kp, __half *__restrict__ out) {
+                                                            int depth, int Kp, __half *__restrict__ out, const int32_t *__restrict__ m_dev, int32_t m_off) {
+  if (m_dev) {                                                  // device-side row count (see GemmParams::m_dev)
+    const int64_t d = (int64_t)(*m_dev) - m_off;
+    M = d < 0 ? 0 : (d < M ? d : M);
+  }
   const int64_t total = M * (int64_t)(Kp / 8);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t m = i / (Kp / 8);
@@ -684,13 +688,14 @@ int onehot_device(const uint8_t *x, int64_t M, int S, int depth, int Kp, void *o
   return dcb_check_launch();
 }
 
-int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, cudaStream_t st) {
+int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int64_t M, int S, int depth, int Kp, void *out, const int32_t *m_dev,
+                         int32_t m_off, cudaStream_t st) {
   if (M == 0) return DCB_OK;
   int64_t blocks = (M * (Kp / 8) + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  if (env == 0) onehot_gather_kernel<9><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
-  else if (env == DCB_ENV_CUBE4) onehot_gather_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
-  else onehot_gather_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out);
+  if (env == 0) onehot_gather_kernel<9><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
+  else if (env == DCB_ENV_CUBE4) onehot_gather_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
+  else onehot_gather_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
   return dcb_check_launch();
 }
 

@@ -80,6 +80,7 @@ class TcResnet:
         self.gemm_events = None     # when a list: (start_event, end_event, algorithmic_flops) per dcb_resnet_gemm launch (bench.py)
         self.gemm_launches = 0
         self._scratch = None        # per-CTA fp32 partial sums of the on-chip K chunking (dcb_resnet_gemm_ex)
+        self._out_cap = None
 
     def _buf(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols)
@@ -118,10 +119,11 @@ class TcResnet:
                                      ptr(layer.bias), layer.scale, ptr(skip_hi), ptr(skip_lo),
                                      1 if relu else 0, ptr(out_hi), ptr(out_lo), None, None, None,
                                      ptr(dot[0]) if dot is not None else None, ptr(dot[1]) if dot is not None else None,
-                                     m, layer.np_, layer.kp, ptr(m_dev), m_off, kc, ptr(self._scratch) if kc else None, st), "dcb_resnet_gemm_ex")
+                                     m, layer.np_, layer.kp, m_dev, m_off, kc, ptr(self._scratch) if kc else None, st), "dcb_resnet_gemm_ex")
         if self.gemm_events is not None:
             ev1 = torch.cuda.Event(enable_timing=True); ev1.record()
-            self.gemm_events.append((ev0, ev1, 2.0 * m * layer.n * layer.k))
+            # (with a device-side row count the host does not know the rows: the caller multiplies flops_per_row by the rows it reads back)
+            self.gemm_events.append((ev0, ev1, None if m_dev is not None else 2.0 * m * layer.n * layer.k))
 
     def _buf32(self, name: str, rows: int, cols: int) -> torch.Tensor:
         key = (name, cols, 32)
@@ -143,40 +145,65 @@ class TcResnet:
         (dcb_onehot_fp16_nodes), skipping the intermediate nnet-input matrix."""
         return self._forward(n, env_id=env_id, arena=arena, ids=ids)
 
-    def _forward(self, n: int, x=None, env_id: int = 0, arena=None, ids=None) -> torch.Tensor:
-        out = torch.empty(n, dtype=torch.float32, device=self.dev)
+    @torch.no_grad()
+    def eval_nodes_dev(self, env_id: int, arena: torch.Tensor, ids: torch.Tensor, n_dev: int, cap: int):
+        """Same as eval_nodes with the row count in DEVICE memory (`n_dev` = address of an int32/uint32, at most `cap`): the whole
+        forward pass is enqueued without the host knowing how many children survived CLOSED (dcb_resnet_gemm_ex's d_m_count).
+        Returns ("dot", partials f32 [cap, n_parts], n_parts, bias) when fc_out is fused -- the search's push kernel adds the tile
+        partials in index order -- else ("h", cost-to-go f32 [cap]).  Rows past the device count are not computed."""
+        if self._out_cap is None or self._out_cap.numel() < cap:
+            self._out_cap = torch.empty(cap, dtype=torch.float32, device=self.dev)
+        fused = self.fuse_fc_out and self.num_blocks > 0
+        width = self.layers[1].np_
+        dpart = self._buf32("dot_partial_dev", cap, width // 256) if fused else None
+        self._forward(cap, env_id=env_id, arena=arena, ids=ids, m_dev=n_dev, out=self._out_cap, dpart_all=dpart)
+        if fused:
+            return ("dot", dpart, width // 256, self.b_out)
+        return ("h", self._out_cap)
+
+    def _forward(self, n: int, x=None, env_id: int = 0, arena=None, ids=None, m_dev: Optional[int] = None, out=None, dpart_all=None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=self.dev)
         st = torch.cuda.current_stream(self.dev).cuda_stream
         sp = self.split
         n_parts = max(1, -(-n // self.chunk))
         part = -(-(-(-n // n_parts)) // 256) * 256          # equal parts, whole 256-row CTA-pair tiles
+        md = dict(m_dev=m_dev) if m_dev is not None else {}
         for i0 in range(0, n, part):
             m = min(part, n - i0)
+            if m_dev is not None:
+                md["m_off"] = i0
             a0 = self._buf("onehot", m, self.k0)
             if x is not None:
                 check(self.lib.dcb_onehot_fp16(ptr(x[i0:i0 + m]), m, self.state_dim, self.depth, self.k0, ptr(a0), st), "dcb_onehot_fp16")
+            elif m_dev is not None:
+                check(self.lib.dcb_onehot_fp16_nodes_ex(env_id, ptr(arena), ids.data_ptr() + 4 * i0, m, self.depth, self.k0, ptr(a0),
+                                                        m_dev, i0, st), "dcb_onehot_fp16_nodes_ex")
             else:
                 check(self.lib.dcb_onehot_fp16_nodes(env_id, ptr(arena), ids.data_ptr() + 4 * i0, m, self.depth, self.k0, ptr(a0), st),
                       "dcb_onehot_fp16_nodes")
             l0, l1 = self.layers[0], self.layers[1]
             h1_hi = self._buf("h1_hi", m, l0.np_)
             h1_lo = self._buf("h1_lo", m, l0.np_) if sp else None
-            self._gemm(l0, a0, None, None, None, True, h1_hi, h1_lo, m, st)            # one-hot input is exact: hi only
+            self._gemm(l0, a0, None, None, None, True, h1_hi, h1_lo, m, st, **md)      # one-hot input is exact: hi only
             width = l1.np_
             x_hi, x_lo = self._buf("x_hi", m, width), (self._buf("x_lo", m, width) if sp else None)
-            self._gemm(l1, h1_hi, h1_lo, None, None, True, x_hi, x_lo, m, st)
+            self._gemm(l1, h1_hi, h1_lo, None, None, True, x_hi, x_lo, m, st, **md)
             t_hi, t_lo = self._buf("t_hi", m, width), (self._buf("t_lo", m, width) if sp else None)
             y_hi, y_lo = self._buf("y_hi", m, width), (self._buf("y_lo", m, width) if sp else None)
             for k in range(self.num_blocks):
                 la, lb = self.layers[2 + 2 * k], self.layers[3 + 2 * k]
-                self._gemm(la, x_hi, x_lo, None, None, True, t_hi, t_lo, m, st)
+                self._gemm(la, x_hi, x_lo, None, None, True, t_hi, t_lo, m, st, **md)
                 if self.fuse_fc_out and k == self.num_blocks - 1:
                     # last residual layer: fc_out (pytorch_models.py:85) is folded into its epilogue -- the [m, 1024] output never
-                    # reaches HBM, only one partial dot product per 256-column tile, added here in a fixed order
-                    dpart = self._buf32("dot_partial", m, width // 256)
-                    self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, None, None, m, st, dot=(self.w_out_padded, dpart))
-                    torch.add(dpart[:m].sum(dim=1), self.b_out, out=out[i0:i0 + m])
+                    # reaches HBM, only one partial dot product per 256-column tile, added in a fixed order (here, or by the
+                    # search's push kernel when the row count lives on the device)
+                    dpart = dpart_all[i0:i0 + m] if dpart_all is not None else self._buf32("dot_partial", m, width // 256)
+                    self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, None, None, m, st, dot=(self.w_out_padded, dpart), **md)
+                    if dpart_all is None:
+                        torch.add(dpart[:m].sum(dim=1), self.b_out, out=out[i0:i0 + m])
                     break
-                self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, y_hi, y_lo, m, st)        # relu(fc(t) + skip)
+                self._gemm(lb, t_hi, t_lo, x_hi, x_lo, True, y_hi, y_lo, m, st, **md)  # relu(fc(t) + skip)
                 x_hi, y_hi = y_hi, x_hi
                 x_lo, y_lo = y_lo, x_lo
             else:

@@ -27,7 +27,8 @@ import numpy as np
 import torch
 
 from ..environments.environment_abstract import Environment, State
-from ..search.bwas_gpu import NONE, BWASGpu
+from .._lib import DcbError
+from ..search.engine import NONE, BWASGpu, SearchEngine
 from ..utils import data_utils, env_utils, misc_utils, nnet_utils, search_utils  # noqa: F401
 
 
@@ -81,70 +82,55 @@ def _env_name(env: Environment) -> str:
     return "lightsout%d" % env.dim if kind == "LightsOut" else "puzzle%d" % (env.dim * env.dim - 1)
 
 
-class Instance:
-    """One search problem = one device-resident engine (astar.py:50-90 keeps heap + dict per instance)."""
-
-    def __init__(self, env: Environment, state: State, heuristic_fn: Callable, weight: float, max_nodes: int):
-        self.env = env
-        self.root_state = state
-        self.heuristic_fn = heuristic_fn
-        self.weight = weight
-        self.max_nodes = max_nodes
-        self.engine: Optional[BWASGpu] = None
-        self.popped_ids: List[int] = []
-
-    def ensure(self, batch_size: int) -> BWASGpu:
-        if self.engine is None or self.engine.B != batch_size:
-            assert self.engine is None, "batch_size must not change during a search"
-            self.engine = BWASGpu(_env_name(self.env), _device_heuristic(self.heuristic_fn, self.env), self.weight, batch_size,
-                                  max_nodes=self.max_nodes, semantics="python")
-            self.engine.reset(self.env.pack([self.root_state])[0])
-        return self.engine
-
-    # ---- Node materialisation -----------------------------------------------------------------------
-    def node_chain(self, node_id: int) -> Node:
-        eng = self.engine
-        ids = [node_id]
-        A = eng.A
-        sp = eng.slot_parent
-        while ids[-1] != 0:
-            ids.append(int(sp[ids[-1] // A].item()) & 0xFFFFFFFF)
-        ids.reverse()
-        states = self.env.unpack(eng.node_states(ids))
-        g = eng.node_g[torch.tensor(ids, device=eng.dev)].cpu().numpy()
-        sv = eng.node_solved[torch.tensor(ids, device=eng.dev)].cpu().numpy()
-        parent: Optional[Node] = None
-        for k, nid in enumerate(ids):
-            parent = Node(states[k], float(g[k]), bool(sv[k]), None if nid == 0 else nid % A, parent)
-        return parent
-
-
 class AStar:
+    """astar.py:232-340.  ALL instances live in one device-resident engine (search/engine.py): one node arena, one CLOSED table
+    keyed per instance, segmented OPEN; a `step` pops every unsolved instance, expands the popped nodes of all of them in one
+    launch, deduplicates, evaluates the survivors of all instances in ONE heuristic call and pushes -- the flattened batch of
+    astar.py:107-113 / :186, without leaving HBM.  One host round trip per step (the instance records)."""
+
     def __init__(self, states: List[State], env: Environment, heuristic_fn: Callable, weights: List[float],
                  max_nodes: Optional[int] = None):
         self.env: Environment = env
-        self.weights: List[float] = weights
+        self.weights: List[float] = list(weights)
+        self.states: List[State] = list(states)
+        self.heuristic_fn = heuristic_fn
         self.step_num: int = 0
         self.timings: Dict[str, float] = {"pop": 0.0, "expand": 0.0, "check": 0.0, "heur": 0.0, "add": 0.0, "itr": 0.0}
-        # every instance owns a device-resident engine: split a total node budget (default 2^26) over the instances
-        mn = int(max_nodes or os.environ.get("DCB_MAX_NODES", max(1 << 16, (1 << 26) // max(1, len(states)))))
-        self.instances: List[Instance] = [Instance(env, s, heuristic_fn, w, mn) for s, w in zip(states, weights)]
-        self._batch_size: Optional[int] = None
+        # total node budget of the shared arena, split evenly over the instances (default 2^26 nodes)
+        self.max_nodes = int(max_nodes or os.environ.get("DCB_MAX_NODES", 1 << 26))
+        self.engine: Optional[SearchEngine] = None
+        self.popped_ids: List[List[int]] = [[] for _ in states]
+        self.heuristic_calls = 0            # engine-level evaluations: one per step whatever the number of instances
 
-    def _engines(self, batch_size: int) -> List[BWASGpu]:
-        return [inst.ensure(batch_size) for inst in self.instances]
+    def _engine(self, batch_size: int) -> SearchEngine:
+        if self.engine is None:
+            n = len(self.states)
+            per_inst = max(self.max_nodes // max(n, 1), 1)
+            self.engine = SearchEngine(_env_name(self.env), _device_heuristic(self.heuristic_fn, self.env), self.weights, batch_size,
+                                       n_inst=n, max_nodes=per_inst * n, semantics="python")
+            self.engine.raise_on_error = False          # reported per instance below
+            self.engine.reset(self.env.pack(self.states))
+            self.heuristic_calls += 1
+        assert self.engine.B == batch_size, "batch_size must not change during a search"
+        return self.engine
 
     def step(self, heuristic_fn: Callable, batch_size: int, include_solved: bool = False, verbose: bool = False):
         t_itr = time.time()
-        engines = self._engines(batch_size)
-        for inst, eng in zip(self.instances, engines):
-            if not include_solved and eng.goal_ids:
+        eng = self._engine(batch_size)
+        eng.profile = bool(verbose)
+        eng.step_all(include_solved=include_solved)
+        self.heuristic_calls += 1
+        stuck = [i for i, rec in enumerate(eng.inst) if rec.done in (2, 3, 4) and rec.n_goals == 0]
+        if stuck:
+            raise DcbError("instance(s) %s stopped without a goal (2 OPEN exhausted, 3 node arena full, 4 OPEN full): %s -- raise max_nodes "
+                           "(now %d nodes for %d instances)" % (stuck[:8], [int(eng.inst[i].done) for i in stuck[:8]], eng.max_nodes, eng.n_inst))
+        popped = eng.popped_ids.cpu().numpy().view(np.uint32)
+        for i, rec in enumerate(eng.inst):
+            if rec.resting:
                 continue
-            before = dict(eng.timings)
-            eng.step()
-            inst.popped_ids.extend(eng.popped_ids[:eng.last_popped].cpu().numpy().view(np.uint32).tolist())
-            for k in ("pop", "expand", "check", "heur", "add"):
-                self.timings[k] += eng.timings[k] - before[k]
+            self.popped_ids[i].extend(popped[i * eng.Bpad: i * eng.Bpad + rec.n_popped].tolist())
+        for k in ("pop", "expand", "check", "heur", "add"):
+            self.timings[k] = eng.timings[k]
         itr = time.time() - t_itr
         self.timings["itr"] += itr
         if verbose:
@@ -153,23 +139,46 @@ class AStar:
                 self.timings["add"], itr))
         self.step_num += 1
 
+    # ---- Node materialisation (only for the nodes the caller asks about) ---------------------------------
+    def node_chain(self, node_id: int) -> Node:
+        eng = self.engine
+        A, npi = eng.A, eng.nodes_per_inst
+        ids = [int(node_id)]
+        while ids[-1] % npi != 0:
+            ids.append(int(eng.slot_parent[ids[-1] // A].item()) & 0xFFFFFFFF)
+        ids.reverse()
+        states = self.env.unpack(eng.node_states(ids))
+        sel = torch.tensor(ids, dtype=torch.int64, device=eng.dev)
+        g = eng.node_g[sel].cpu().numpy()
+        sv = eng.node_solved[sel].cpu().numpy()
+        parent: Optional[Node] = None
+        for k, nid in enumerate(ids):
+            parent = Node(states[k], float(g[k]), bool(sv[k]), None if k == 0 else nid % A, parent)
+        return parent
+
     def has_found_goal(self) -> List[bool]:
-        return [inst.engine is not None and len(inst.engine.goal_ids) > 0 for inst in self.instances]
+        if self.engine is None:
+            return [False] * len(self.states)
+        return [rec.n_goals > 0 for rec in self.engine.inst]
+
+    def _goal_ids(self, inst_idx: int) -> List[int]:
+        ids = self.popped_ids[inst_idx]
+        if not ids or self.engine is None:
+            return []
+        sv = self.engine.node_solved[torch.tensor(ids, dtype=torch.int64, device=self.engine.dev)].cpu().numpy()
+        return [i for i, s in zip(ids, sv) if s]
 
     def get_goal_nodes(self, inst_idx) -> List[Node]:
-        inst = self.instances[inst_idx]
-        return [inst.node_chain(g) for g in (inst.engine.goal_ids if inst.engine else [])]
+        return [self.node_chain(g) for g in self._goal_ids(inst_idx)]
 
     def get_goal_node_smallest_path_cost(self, inst_idx) -> Node:
-        inst = self.instances[inst_idx]
-        return inst.node_chain(inst.engine.goal_id)
+        return self.node_chain(self.engine.inst[inst_idx].goal_id)
 
     def get_num_nodes_generated(self, inst_idx: int) -> int:
-        eng = self.instances[inst_idx].engine
-        return eng.nodes_generated if eng else 0
+        return int(self.engine.inst[inst_idx].nodes_generated) if self.engine else 0
 
     def get_popped_nodes(self) -> List[List[Node]]:
-        return [[inst.node_chain(i) for i in inst.popped_ids] for inst in self.instances]
+        return [[self.node_chain(i) for i in ids] for ids in self.popped_ids]
 
 
 # =====================================================================================================
@@ -189,7 +198,7 @@ def main(argv: Optional[List[str]] = None):
                         help="States evaluated by the neural network at a time; does not affect results")
     parser.add_argument("--verbose", action="store_true", default=False, help="Set for verbose")
     parser.add_argument("--debug", action="store_true", default=False, help="Set when debugging")
-    parser.add_argument("--nnet_precision", type=str, default=None, help="fp32 (default) | tf32 | bf16 (cuBLAS) | fp16x3 | fp16 (hand-written tcgen05)")
+    parser.add_argument("--nnet_precision", type=str, default=None, help="fp16x3 (default: hand-written tcgen05 layers, fp32-parity) | fp32 | tf32 | bf16 (cuBLAS) | fp16 (tcgen05, reduced)")
     parser.add_argument("--max_nodes", type=int, default=1 << 26, help="Node arena capacity per search")
     parser.add_argument("--num_states", type=int, default=None, help="Solve only the first N states (after --start_idx)")
     args = parser.parse_args(argv)
@@ -199,8 +208,10 @@ def main(argv: Optional[List[str]] = None):
     results_file = "%s/results.pkl" % args.results_dir
     output_file = "%s/output.txt" % args.results_dir
     stdout_prev = sys.stdout
+    rank = int(os.environ.get("RANK", 0))
     if not args.debug:
-        sys.stdout = data_utils.Logger(output_file, "w")
+        # under torchrun only rank 0 owns output.txt (it prints every state's line after the gather); the others keep a private log
+        sys.stdout = data_utils.Logger(output_file if rank == 0 else "%s/output.rank%d.txt" % (args.results_dir, rank), "w")
     try:
         input_data = pickle.load(open(args.states, "rb"))
         states: List[State] = input_data["states"][args.start_idx:]
@@ -219,7 +230,12 @@ def main(argv: Optional[List[str]] = None):
         results["paths"] = paths
         results["times"] = times
         results["num_nodes_generated"] = num_nodes_gen
-        if int(os.environ.get("RANK", 0)) == 0:
+        tc = getattr(getattr(args, "_heuristic_fn", None), "device_fn", None)
+        if hasattr(tc, "gemm_launches"):
+            print("nnet: precision=%s kernel=dcb_resnet_gemm (tcgen05) launches=%d" % (tc.mode, tc.gemm_launches))
+        else:
+            print("nnet: precision=%s (cuBLAS via PyTorch)" % (args.nnet_precision or os.environ.get("DCB_NNET_PRECISION", "fp32")))
+        if rank == 0:
             pickle.dump(results, open(results_file, "wb"), protocol=-1)
     finally:
         sys.stdout = stdout_prev
@@ -230,8 +246,10 @@ def _load_heuristic(args, env: Environment):
     print("device: %s, devices: %s, on_gpu: %s" % (device, devices, on_gpu))
     if not on_gpu:
         raise RuntimeError("the BWAS engine is CUDA-only; no GPU is visible and there is no CPU fallback")
-    return nnet_utils.load_heuristic_fn(args.model_dir, device, on_gpu, env.get_nnet_model(), env, clip_zero=True,
-                                        batch_size=args.nnet_batch_size, precision=args.nnet_precision)
+    fn = nnet_utils.load_heuristic_fn(args.model_dir, device, on_gpu, env.get_nnet_model(), env, clip_zero=True,
+                                      batch_size=args.nnet_batch_size, precision=args.nnet_precision)
+    args._heuristic_fn = fn
+    return fn
 
 
 def bwas_python(args, env: Environment, states: List[State]):
@@ -255,7 +273,7 @@ def bwas_python(args, env: Environment, states: List[State]):
         print("Times - %s, num_itrs: %i" % (timing_str, num_itrs))
         print("State: %i, SolnCost: %.2f, # Moves: %i, # Nodes Gen: %s, Time: %.2f" % (
             state_idx, path_cost, len(soln), format(n_gen, ","), solve_time))
-        astar.instances[0].engine = None        # release HBM before the next state
+        astar.engine = None                     # release HBM before the next state
     return solns, paths, times, num_nodes_gen
 
 

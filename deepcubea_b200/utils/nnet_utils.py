@@ -23,13 +23,15 @@ def get_available_gpu_nums() -> List[int]:
 
 
 def get_device() -> Tuple[torch.device, List[int], bool]:
-    """CUDA device 0 of the visible set when there is one (the reference requires CUDA_VISIBLE_DEVICES to be set;
-    here an unset variable means "all GPUs")."""
+    """The process's CURRENT CUDA device when there is one (cuda:0 unless the caller picked another with
+    torch.cuda.set_device -- one process per GPU under torchrun; the reference always answers cuda:0 because it isolates its
+    per-GPU runner processes with CUDA_VISIBLE_DEVICES, nnet_utils.py:122-130).  An unset CUDA_VISIBLE_DEVICES means "all GPUs"
+    (the reference requires it to be set)."""
     devices = get_available_gpu_nums()
     if torch.cuda.is_available():
         if not devices:
             devices = list(range(torch.cuda.device_count()))
-        return torch.device("cuda:0"), devices, True
+        return torch.device("cuda", torch.cuda.current_device()), devices, True
     return torch.device("cpu"), devices, False
 
 
@@ -86,17 +88,21 @@ def load_heuristic_fn(nnet_dir: str, device: torch.device, on_gpu: bool, nnet: n
                       clip_zero: bool = False, gpu_num: int = -1, batch_size: Optional[int] = None,
                       precision: Optional[str] = None):
     """nnet_utils.py:206-221.  `precision` (or $DCB_NNET_PRECISION) selects the inference arithmetic of the
-    network: fp32 (cuBLAS, default) | tf32 | bf16 | fp16x3 (tcgen05, fp32-parity) | fp16 (tcgen05)."""
+    network: fp16x3 (hand-written tcgen05 layers, fp32-parity: max |err| 3e-5 vs the fp64 network; the default on a GPU) | fp32
+    (cuBLAS SGEMM, the reference's arithmetic) | tf32 | bf16 | fp16 (tcgen05, reduced precision).  Networks the tcgen05 path does
+    not encode (no one-hot input) fall back to fp32 unless a precision was asked for explicitly."""
     if gpu_num >= 0 and on_gpu:
         os.environ["CUDA_VISIBLE_DEVICES"] = str(gpu_num)
     nnet = load_nnet("%s/model_state_dict.pt" % nnet_dir, nnet, device=device)
     nnet.eval()
     nnet.to(device)
     if on_gpu:
-        mode = precision or os.environ.get("DCB_NNET_PRECISION", "fp32")
+        mode = precision or os.environ.get("DCB_NNET_PRECISION")
+        if mode is None:
+            mode = "fp16x3" if getattr(nnet, "one_hot_depth", 0) > 0 else "fp32"
         if mode in ("fp16x3", "fp16"):            # hand-written tcgen05 dense layers
             from ..nnet.tc_resnet import TcResnet
-            tc = TcResnet(nnet, device, mode=mode, chunk=batch_size or (1 << 16))
+            tc = TcResnet(nnet, device, mode=mode, chunk=max(batch_size or 0, 1 << 18))
             fn = get_heuristic_fn(nnet, device, env, clip_zero=clip_zero, batch_size=batch_size)
             fn.device_fn = tc
             return fn

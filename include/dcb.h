@@ -122,14 +122,16 @@ int dcb_closed_clear(void *d_table, int64_t capacity, void *stream);
 /* Insert-or-improve for a batch of m candidate nodes whose states already sit in the arena.
  *   d_hash [m] u64, d_g [m] u32 (path cost = depth), node id of candidate i = first_id + i.
  *   d_valid [m] u8 or NULL: candidates with valid==0 are ignored (padding).
- * Result d_keep[i] = 1 iff candidate i is (a) a state never seen, or (b) a seen state reached with a
- * STRICTLY smaller g -- exactly the keep rule of :246-261 -- and, among duplicates inside this batch, it is
- * the one with the smallest (g, id).  Equal hashes are verified by comparing the S state bytes in the
- * arena; on a true 64-bit collision the candidate is kept (never wrongly dropped).
- * d_slot [m] u32 is scratch.  Two launches (insert, resolve). */
+ * Result d_keep[i] = 1 iff the reference's child-order loop (:246-261; remove_in_closed, astar.py:78-90) keeps candidate i:
+ * its state was never seen, or it is reached with a STRICTLY smaller g than the table holds AT THAT POINT OF THE LOOP --
+ * i.e. smaller than the value stored before this batch and than every earlier (lower id) candidate of the same state in
+ * this batch.  The table ends up holding the smallest (g, id) per state.  Equal hashes are verified by comparing the S
+ * state bytes in the arena; on a true 64-bit collision the candidate is kept (never wrongly dropped).
+ * d_scratch: dcb_closed_scratch_bytes(m) bytes, 16-byte aligned.  Four launches (probe, min, resolve, in-batch fix-up). */
+int64_t dcb_closed_scratch_bytes(int64_t m);
 int dcb_closed_insert(int env, void *d_table, int64_t capacity, const uint8_t *d_arena,
                       const uint64_t *d_hash, const uint32_t *d_g, const uint8_t *d_valid, uint32_t first_id,
-                      int64_t m, uint32_t *d_slot, uint8_t *d_keep, uint32_t *d_num_entries, void *stream);
+                      int64_t m, void *d_scratch, uint8_t *d_keep, uint32_t *d_num_entries, void *stream);
 /* Re-insert every entry of an old table into a (larger, cleared) new one. */
 int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int64_t new_capacity, void *stream);
 
@@ -141,17 +143,30 @@ int dcb_closed_rehash(const void *d_old, int64_t old_capacity, void *d_new, int6
  * two 4096-bucket histogram passes over key bits 31..20 / 19..8, a single-block finish on the boundary
  * bucket, one partition pass.  Ties on cost break towards the smaller node id (the reference's C++ heap
  * order is unspecified; Python's heapq is FIFO, which this matches). */
-typedef struct dcb_open_state {      /* lives in device memory; the host may copy it back to inspect     */
-  uint32_t size;                     /* live entries in d_key / d_id                                      */
-  uint32_t n_popped;                 /* entries returned by the last pop                                  */
-  uint32_t thr_key, thr_id;          /* last pop: select threshold (everything <= it was removed)         */
-  uint32_t min_key;                  /* last pop: smallest key popped == popped[0]->cost                  */
-  uint32_t goal_id;                  /* cheapest solved node popped so far (0xffffffff = none)            */
-  uint32_t goal_key;
-  uint32_t done;                     /* 1: termination rule of :205-208 (or :191-193) fired; 2: OPEN empty */
-  uint32_t overflow;                 /* a push ran past `capacity`                                         */
-  uint32_t need, prefix, cand_count, n_holes, n_surv, take_all, n_at_pop;   /* pop-internal              */
-} dcb_open_state;
+typedef struct dcb_search_inst {     /* one per problem instance; lives in device memory; the host may copy it back (128 bytes) */
+  uint32_t open_size;                /* live entries of this instance's OPEN segment                               */
+  uint32_t n_popped;                 /* nodes returned by the last pop (C++ semantics: after the break at the first solved one) */
+  uint32_t n_expand;                 /* parents the current iteration expands (0 once `done` fired / the arena is full) */
+  uint32_t min_key;                  /* last pop: smallest key popped == popped[0]->cost                          */
+  uint32_t goal_id;                  /* C++: cheapest solved node popped so far; Python: solved popped node of smallest path
+                                        cost (astar.py:327-333); 0xffffffff = none                                */
+  uint32_t goal_key;                 /* C++: its cost bits; Python: its path cost                                  */
+  uint32_t done;                     /* 0 running | 1 finished (:205-208 / :191-193; Python: a solved node was popped, astar.py:73)
+                                        | 2 OPEN exhausted | 3 node arena full | 4 OPEN segment full               */
+  uint32_t n_goals;                  /* Python: solved nodes popped so far (Instance.goal_nodes)                   */
+  uint32_t next_slot;                /* next free arena slot, counted inside the instance's own slot range         */
+  uint32_t base_slot;                /* this iteration's first child record (instance-local slot)                  */
+  uint32_t iterations;               /* pops so far                                                                */
+  uint32_t tile_off;                 /* first 32-parent tile of this instance in the current iteration's tile list */
+  uint64_t nodes_generated;          /* the reference's counter: C++ 1 + sum popped*A incl. the terminating iteration (:166, :266);
+                                        Python sum popped*A (astar.py:168)                                         */
+  uint64_t nodes_expanded;           /* children actually materialised in the arena                                */
+  uint32_t thr_key, thr_id;          /* last pop: select threshold (everything <= it was removed)                  */
+  uint32_t need, prefix, cand_count, n_holes, n_surv, take_all, n_at_pop, n_take, resting;   /* pop-internal     */
+  uint32_t overflow;                 /* a push ran past the segment's capacity                                     */
+  uint32_t reserved[4];
+} dcb_search_inst;
+typedef dcb_search_inst dcb_open_state;   /* a stand-alone OPEN queue is a search instance that uses only the OPEN fields */
 int dcb_open_clear(dcb_open_state *d_state, void *stream);
 /* Append m entries with cost d_cost[i] (float32 >= 0) and node id (d_ids ? d_ids[i] : first_id + i);
  * entries with d_keep[i]==0 are skipped (d_keep may be NULL). */
@@ -163,7 +178,7 @@ int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int6
  * first SOLVED entry in cost order (the `break` at :190-203; the entries behind it go back to OPEN) and the
  * goal bookkeeping / termination rule of :186-208 is applied to d_state (goal_id, goal_key, done).
  * d_node_solved [node id] u8.  d_scratch: dcb_open_scratch_bytes(capacity, batch) bytes, 16-byte aligned. */
-int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch);
+int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch);   /* one instance; see dcb_search_pop_scratch_bytes */
 int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, int32_t batch,
                  int stop_at_goal, const uint8_t *d_node_solved, uint32_t *d_popped_ids, void *d_scratch,
                  void *stream);
@@ -193,6 +208,73 @@ int dcb_compute_cost(const float *d_h, const uint32_t *d_ids, const uint32_t *d_
  * moves root->goal into d_moves [max_len] and the length into d_len (-1 if max_len was too small). */
 int dcb_reconstruct_path(int env, const uint32_t *d_slot_parent, uint32_t goal_id, int32_t max_len,
                          uint8_t *d_moves, int32_t *d_len, void *stream);
+
+/* ---- device-driven search iteration ------------------------------------------------------------------
+ * One BWAS iteration (parallel_weighted_astar.cpp:169-330) / one AStar.step over ALL instances (astar.py:256-317) as a fixed
+ * sequence of launches whose sizes live in device memory: nothing between the pop and the push needs the host, so an
+ * iteration can be enqueued before the previous one has finished (or be captured in a CUDA graph).
+ *
+ * n_inst problem instances share one node arena, one CLOSED table (keys mixed with the instance number) and segmented OPEN
+ * arrays.  Instance i owns arena slots [i*slots_per_inst, (i+1)*slots_per_inst); node id = global slot * A + move; its root is
+ * node i*slots_per_inst*A.  The pop stage leaves, per iteration, a list of 32-parent TILES: tile t = {src, dst_slot, count,
+ * inst} -- parents d_popped_ids[src .. src+count), children written to arena slots dst_slot .. dst_slot+count-1 (dst_slot is
+ * a multiple of dcb_env_slot_align).  Candidate c of the iteration = child (c % A) of parent lane (c / A) % 32 of tile c / (32*A). */
+typedef struct dcb_step_plan {       /* one per engine; device memory; written by the pop stage, read by the later ones (64 bytes) */
+  uint32_t n_tiles;                  /* tiles of this iteration                                                    */
+  uint32_t n_parents;                /* parents expanded (sum of n_expand)                                         */
+  uint32_t n_kept;                   /* children that survived CLOSED == rows for the cost-to-go network           */
+  uint32_t n_ambiguous;              /* CLOSED-internal: candidates decided by the in-batch fix-up                 */
+  uint32_t closed_entries;           /* occupied CLOSED slots                                                      */
+  uint32_t n_running;                /* instances with done == 0 after this pop                                    */
+  uint32_t error;                    /* sticky bits: 1 arena full, 2 OPEN segment full, 4 CLOSED table full        */
+  uint32_t reserved0;
+  uint64_t total_kept;               /* since the last reset                                                       */
+  uint64_t total_expanded;           /* children materialised since the last reset                                 */
+  uint64_t reserved1[2];
+} dcb_step_plan;
+
+typedef struct dcb_search_ctx {      /* HOST struct: geometry + the device buffers of one engine (all caller-owned)  */
+  int32_t env, n_inst, batch, semantics;   /* semantics 0: C++ program (parallel_weighted_astar.cpp), 1: Python AStar class   */
+  uint32_t slots_per_inst;           /* multiple of 32; n_inst * slots_per_inst * A < 2^32                         */
+  uint32_t open_per_inst;            /* OPEN entries per instance                                                  */
+  int64_t closed_capacity;           /* power of two, <= 2^31                                                      */
+  uint8_t *d_arena;                  /* [n_inst*slots_per_inst*A][S]                                               */
+  uint32_t *d_node_g;                /* [nodes] path cost                                                          */
+  uint8_t *d_node_solved;            /* [nodes]                                                                    */
+  uint32_t *d_slot_parent;           /* [slots] node id of the slot's parent                                       */
+  void *d_closed;                    /* dcb_closed_bytes(closed_capacity)                                          */
+  uint32_t *d_open_key, *d_open_id;  /* [n_inst][open_per_inst]                                                    */
+  dcb_search_inst *d_inst;           /* [n_inst]                                                                   */
+  dcb_step_plan *d_plan;
+  const float *d_weights;            /* [n_inst] path-cost weight of each instance (AStar(states, env, fn, weights)) */
+  uint32_t *d_popped_ids;            /* [n_inst][ceil32(batch)]                                                    */
+  uint32_t *d_tiles;                 /* [n_inst*ceil(batch/32)] x 4 u32                                            */
+  uint64_t *d_hash;                  /* [max candidates = n_inst*ceil32(batch)*A]                                  */
+  uint32_t *d_kept_ids;              /* [max candidates]                                                           */
+  void *d_pop_scratch;               /* dcb_search_pop_scratch_bytes                                               */
+  void *d_closed_scratch;            /* dcb_closed_scratch_bytes(max candidates)                                   */
+} dcb_search_ctx;
+int64_t dcb_search_pop_scratch_bytes(int32_t n_inst, int64_t open_per_inst, int32_t batch);
+/* Roots: d_roots [n_inst][S].  Clears the instance records and the plan, writes the roots into the arena; C++ semantics: root
+ * into CLOSED with g = 0 and into OPEN with cost 0 (:160-162), nodes_generated = 1 (:166); Python semantics: root NOT in CLOSED
+ * (astar.py:50-62), d_kept_ids[0..n_inst) = the root ids and plan.n_kept = n_inst so that the caller evaluates them and calls
+ * dcb_search_push (root cost = heuristic, astar.py:244-249).  The CLOSED table must have been cleared (dcb_closed_clear). */
+int dcb_search_reset(const dcb_search_ctx *ctx, const uint8_t *d_roots, void *stream);
+/* Pop stage: segmented exact top-`batch` pop of every running instance (Python: every instance without a goal node, or all with
+ * include_solved, astar.py:263-265), goal / termination bookkeeping on the device, slot assignment, tile list, plan. */
+int dcb_search_pop(const dcb_search_ctx *ctx, int include_solved, void *stream);
+/* Expand every tile: children + is_solved + hash (dcb_expand_indexed's kernel), depth and parent link of every child. */
+int dcb_search_expand(const dcb_search_ctx *ctx, void *stream);
+/* CLOSED insert-or-improve of every candidate (dcb_closed_insert's rule, keyed per instance); survivors are appended
+ * (unordered) to d_kept_ids, plan.n_kept counts them. */
+int dcb_search_closed(const dcb_search_ctx *ctx, void *stream);
+/* cost = max(h,0)*(!solved) + weight*g (dcb_compute_cost) for d_kept_ids[0..plan.n_kept) and push onto each node's instance's
+ * OPEN.  The heuristic comes either as d_h [rows] or as the fused fc_out partials of dcb_resnet_gemm (d_dot_partial
+ * [rows][n_parts], summed in index order, + dot_bias). */
+int dcb_search_push(const dcb_search_ctx *ctx, const float *d_h, const float *d_dot_partial, int32_t n_parts, float dot_bias,
+                    void *stream);
+/* Moves root -> node of the instance that owns `node_id` (dcb_reconstruct_path for a shared arena). */
+int dcb_search_path(const dcb_search_ctx *ctx, uint32_t node_id, int32_t max_len, uint8_t *d_moves, int32_t *d_len, void *stream);
 
 /* ---- cost-to-go network (utils/pytorch_models.py:45-86), dense layers on tcgen05 tensor cores ------
  * Eval-mode BatchNorm is folded into the preceding Linear by the caller (deepcubea_b200/nnet/tc_resnet.py).
@@ -235,6 +317,9 @@ int dcb_onehot_fp16(const uint8_t *d_nnet_in, int64_t m, int32_t state_dim, int3
  * (cube3.py:77-85) and the one-hot encoding in one pass -- the form the A* loop uses for the children that survived CLOSED. */
 int dcb_onehot_fp16_nodes(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, int32_t depth, int32_t k_padded,
                           void *d_out, void *stream);
+/* Same with a DEVICE-side row count: rows = clamp(*d_m_count - m_offset, 0, m) (see dcb_resnet_gemm_ex). */
+int dcb_onehot_fp16_nodes_ex(int env, const uint8_t *d_arena, const uint32_t *d_ids, int64_t m, int32_t depth, int32_t k_padded,
+                             void *d_out, const int32_t *d_m_count, int32_t m_offset, void *stream);
 /* fc_out (pytorch_models.py:85): d_out[m] = sum_{n<n_valid} (x_hi+x_lo)[m][n] * d_w[n] + bias, fp32. */
 int dcb_rowdot(const void *d_x_hi, const void *d_x_lo, const float *d_w, float bias, int64_t m, int32_t n_valid, int32_t ld,
                float *d_out, void *stream);

@@ -36,7 +36,8 @@ def slot_align(state_dim: int, num_moves: int) -> int:
 
 
 def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], weight: float, batch_size: int,
-         batch_dedup: str = "min", max_iters: Optional[int] = None, keep_trace: bool = False) -> Dict:
+         batch_dedup: str = "sequential", max_iters: Optional[int] = None, keep_trace: bool = False,
+         mutate_stored: bool = True) -> Dict:
     A, S = env.num_moves, env.state_dim
     align = slot_align(S, A)
     w32 = np.float32(weight)
@@ -44,7 +45,12 @@ def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], 
     depth: Dict[int, int] = {0: 0}
     solved: Dict[int, bool] = {0: bool(env.is_solved(states[0][None])[0])}
     parent: Dict[int, int] = {}
-    closed: Dict[bytes, List[int]] = {states[0].tobytes(): [0, 0]}      # state -> [best depth, node id]
+    closed: Dict[bytes, List[int]] = {states[0].tobytes(): [0, 0, 0]}   # state -> [best depth, its node id, STORED node id]
+    # `(*found)->depth / parentMove / parent = node->...` (:255-257): the node object stored in CLOSED (the first one of its
+    # state) takes over the improving node's depth and parent link.  `link[id]` = the node whose (parent, move) the stored node
+    # `id` now carries; path reconstruction (:336-341) follows it.  The depth half of the mutation only matters if the stored
+    # node is expanded AFTER being improved; its children then carry the improved depth + 1 (restated via `depth[stored]`).
+    link: Dict[int, int] = {}
     open_heap = [(np.float32(0.0), 0)]                                   # (cost f32, id)
     next_slot = 1
     nodes_generated = 1
@@ -95,9 +101,11 @@ def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], 
                 key = flat[i].tobytes()
                 e = closed.get(key)
                 if e is None:
-                    closed[key] = [dep[i], nid]; keep[i] = True
+                    closed[key] = [dep[i], nid, nid]; keep[i] = True
                 elif e[0] > dep[i]:
                     e[0] = dep[i]; e[1] = nid; keep[i] = True
+                    if mutate_stored:
+                        link[e[2]] = nid; depth[e[2]] = dep[i]
         else:
             best: Dict[bytes, int] = {}
             for i in range(len(ids)):
@@ -107,8 +115,10 @@ def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], 
                     best[key] = i
             for key, i in best.items():
                 e = closed.get(key)
-                if e is None or e[0] > dep[i]:
-                    closed[key] = [dep[i], ids[i]]; keep[i] = True
+                if e is None:
+                    closed[key] = [dep[i], ids[i], ids[i]]; keep[i] = True
+                elif e[0] > dep[i]:
+                    e[0] = dep[i]; e[1] = ids[i]; keep[i] = True
         kept = [i for i in range(len(ids)) if keep[i]]
         # ---- heuristic + cost (:237, 275-300): values only matter for kept children ----
         for i, nid in enumerate(ids):
@@ -126,10 +136,11 @@ def bwas(env, start: np.ndarray, heuristic: Callable[[np.ndarray], np.ndarray], 
         moves = []
         nid = goal[1]
         while nid != 0:                                                   # :336-341
-            moves.append(nid % A)
-            nid = parent[nid]
+            src = link.get(nid, nid)                                      # a stored node that was improved carries the improver's link
+            moves.append(src % A)
+            nid = parent[src]
         moves.reverse()
-    return {"moves": moves, "nodes_generated": nodes_generated, "iterations": iters, "done": done,
+    return {"moves": moves, "nodes_generated": nodes_generated, "iterations": iters, "done": done, "links": len(link),
             "goal_id": None if goal is None else goal[1], "trace": trace, "open_size": len(open_heap),
             "closed_size": len(closed)}
 

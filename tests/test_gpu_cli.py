@@ -79,7 +79,7 @@ def test_astar_class_api_python_semantics():
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(WEIGHTS_DIR, "model_state_dict.pt")), reason="trained weights not present (assets/)")
-@pytest.mark.parametrize("language,precision", [("cuda", "fp16x3"), ("python", "fp32")])
+@pytest.mark.parametrize("language,precision", [("cuda", None), ("python", "fp32")])
 def test_cli_solves_reference_test_states(tmp_path, golden_dir, language, precision):
     """`python search_methods/astar.py ...` on the first states of data/cube3/test: valid solutions, lengths within the
     reference's own optimality gap (<= optimal + 4, results/cube3), reference results.pkl schema."""
@@ -93,7 +93,7 @@ def test_cli_solves_reference_test_states(tmp_path, golden_dir, language, precis
     out = tmp_path / "res"
     cmd = [sys.executable, os.path.join(ROOT, "search_methods", "astar.py"), "--states", str(tmp_path / "in.pkl"), "--model", WEIGHTS_DIR,
            "--env", "cube3", "--weight", "0.6", "--batch_size", "2000", "--results_dir", str(out), "--language", language,
-           "--nnet_batch_size", "10000", "--nnet_precision", precision, "--max_nodes", str(1 << 24)]
+           "--nnet_batch_size", "10000", "--max_nodes", str(1 << 24)] + (["--nnet_precision", precision] if precision else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     res = pickle.load(open(out / "results.pkl", "rb"))
@@ -108,6 +108,10 @@ def test_cli_solves_reference_test_states(tmp_path, golden_dir, language, precis
         assert res["num_nodes_generated"][i] > 0 and res["times"][i] > 0
     text = open(out / "output.txt").read()
     assert text.count("State: ") == n and "# Nodes Gen:" in text
+    if precision is None:           # the reference's command line, no extra flag: the hand-written tcgen05 layers are the default
+        import re
+        m = re.search(r"nnet: precision=fp16x3 kernel=dcb_resnet_gemm \(tcgen05\) launches=(\d+)", text)
+        assert m and int(m.group(1)) > 0, text[-500:]
     cmp = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "compare_solutions.py"), "--soln1", str(out / "results.pkl"),
                           "--soln2", str(out / "results.pkl")], capture_output=True, text=True, cwd=ROOT)
     assert cmp.returncode == 0 and "100.00% soln2 equal to soln1" in cmp.stdout

@@ -17,6 +17,10 @@ def _u32(t):
     return t.cpu().numpy().view(np.uint32)
 
 
+def _scratch(lib, m):
+    return torch.empty(int(lib.dcb_closed_scratch_bytes(m)), dtype=torch.uint8, device="cuda")
+
+
 def test_closed_insert_or_improve_matches_dict_model():
     from deepcubea_b200 import _lib
     lib = _lib.load(); p = _lib.ptr
@@ -40,17 +44,14 @@ def test_closed_insert_or_improve_matches_dict_model():
         arena[next_id * 54:(next_id + m) * 54] = torch.from_numpy(states.reshape(-1)).cuda()
         hs = torch.from_numpy(O.state_hash64(states).view(np.int64)).cuda()
         gd = torch.from_numpy(g.view(np.int32)).cuda()
-        slot = torch.empty(m, dtype=torch.int32, device="cuda"); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
+        slot = _scratch(lib, m); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
         _lib.check(lib.dcb_closed_insert(0, p(table), cap, p(arena), p(hs), p(gd), None, next_id, m, p(slot), p(keep), p(counter), st))
         keep = keep.cpu().numpy().astype(bool)
-        # model: within the batch only the best (g, id) of each state may survive, and only if it beats what is stored
-        best = {}
+        # model: the reference's child-order loop (parallel_weighted_astar.cpp:246-261; remove_in_closed, astar.py:78-90) -- kept
+        # iff unseen or strictly cheaper than what the table holds when the loop reaches the candidate
+        exp = np.zeros(m, bool)
         for i in range(m):
             k = states[i].tobytes()
-            if k not in best or (g[i], i) < (g[best[k]], best[k]):
-                best[k] = i
-        exp = np.zeros(m, bool)
-        for k, i in best.items():
             if k not in model or model[k] > g[i]:
                 model[k] = g[i]; exp[i] = True
         assert np.array_equal(keep, exp), "round %d" % rnd
@@ -67,7 +68,7 @@ def test_closed_insert_or_improve_matches_dict_model():
     arena2 = torch.cat([arena[:next_id * 54], torch.from_numpy(states.reshape(-1)).cuda(), torch.zeros(64, dtype=torch.uint8, device="cuda")])
     hs = torch.from_numpy(O.state_hash64(states).view(np.int64)).cuda()
     gd = torch.from_numpy(np.array([model[k] for k in keys], np.uint32).view(np.int32)).cuda()
-    slot = torch.empty(m, dtype=torch.int32, device="cuda"); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
+    slot = _scratch(lib, m); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
     _lib.check(lib.dcb_closed_insert(0, p(table2), cap2, p(arena2), p(hs), p(gd), None, next_id, m, p(slot), p(keep), None, st))
     assert int(keep.sum()) == 0
     gd2 = (gd - 1).clamp(min=0)                               # strictly smaller g re-opens (parallel_weighted_astar.cpp:255-261)
@@ -87,7 +88,7 @@ def test_closed_hash_collision_is_kept_not_dropped():
     _lib.check(lib.dcb_closed_clear(p(table), cap, st))
     hs = torch.tensor([12345, 12345], dtype=torch.int64, device="cuda")           # fake equal hashes
     g = torch.tensor([2, 2], dtype=torch.int32, device="cuda")
-    slot = torch.empty(2, dtype=torch.int32, device="cuda"); keep = torch.empty(2, dtype=torch.uint8, device="cuda")
+    slot = _scratch(lib, 2); keep = torch.empty(2, dtype=torch.uint8, device="cuda")
     _lib.check(lib.dcb_closed_insert(0, p(table), cap, p(arena), p(hs), p(g), None, 0, 2, p(slot), p(keep), None, st))
     assert keep.cpu().tolist() == [1, 1]
     arena2 = torch.from_numpy(np.concatenate([a, a, np.zeros(64, np.uint8)])).cuda()   # a true duplicate is dropped
@@ -104,7 +105,7 @@ def test_open_push_pop_matches_heap_model(batch, stop):
     cap = 1 << 16
     n_nodes = 40000
     key = torch.empty(cap, dtype=torch.int32, device="cuda"); ids = torch.empty(cap, dtype=torch.int32, device="cuda")
-    state = torch.zeros(16, dtype=torch.int32, device="cuda")
+    state = torch.zeros(_lib.INST_WORDS, dtype=torch.int32, device="cuda")
     scratch = torch.empty(int(lib.dcb_open_scratch_bytes(cap, batch)) + 16, dtype=torch.uint8, device="cuda")
     popped = torch.empty(batch, dtype=torch.int32, device="cuda")
     solved = (rng.rand(n_nodes) < 0.002).astype(np.uint8)
