@@ -224,6 +224,8 @@ def run_ours(args):
     all_states, states_desc = workload_states(wl, n_inst * world)
     states = all_states[sharding.shard_indices(len(all_states), rank, world)]
 
+    trace = os.environ.get("DCB_BENCH_TRACE") == "1"       # per-iteration wall times on stderr (debugging aid; step() ends with a sync)
+
     def run_window(k_full, cursor):
         """Search iterations over consecutive start states until k_full FULL-BATCH iterations were materialised.
         Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
@@ -236,8 +238,14 @@ def run_ours(args):
             if cursor["fresh"]:
                 eng.reset(states[cursor["i"] % len(states)]); cursor["fresh"] = False
             before = eng.nodes_expanded
+            if trace:
+                t_it = time.perf_counter(); cap0 = eng.closed_cap
             eng.step(); iters += 1
             got = eng.nodes_expanded - before
+            if trace:
+                print("  it %3d %7.2f ms  popped %6d kept %7d  open %9d  closed 2^%d%s" % (
+                    iters, (time.perf_counter() - t_it) * 1e3, eng.last_popped, eng.last_kept, int(eng.inst[0].open_size), int(np.log2(cap0)),
+                    " -> 2^%d" % int(np.log2(eng.closed_cap)) if eng.closed_cap != cap0 else ""), file=sys.stderr)
             nodes += got
             if got == BATCH * A:
                 full += 1

@@ -153,6 +153,11 @@ class SearchEngine:
         # size needs; the largest table holds every node at load <= 0.5
         self.closed_cap_max = min(_next_pow2(2 * self.max_nodes), 1 << 31)
         self.closed_cap_min = min(self.closed_cap_max, _next_pow2(max(8 * self.max_cand, 1 << 16)))
+        # storage for every table size is reserved up front (an allocation inside the search loop stalls the stream): sizes
+        # alternate between two buffers so that a table and its successor never overlap during the rehash
+        with torch.cuda.device(dev):
+            self._closed_bufs = [torch.empty(self.closed_cap_max * 2, dtype=i64, device=dev),
+                                 torch.empty(max(self.closed_cap_max, 2), dtype=i64, device=dev)]
         self.closed_cap = 0
         self.closed = None
         self._alloc_closed(self.closed_cap_min)
@@ -183,7 +188,8 @@ class SearchEngine:
         return torch.cuda.current_stream(self.dev).cuda_stream
 
     def _alloc_closed(self, cap: int) -> None:
-        self.closed = torch.empty(cap * 2, dtype=torch.int64, device=self.dev)
+        level = (self.closed_cap_max // cap).bit_length() - 1          # 0 = the largest table
+        self.closed = self._closed_bufs[level & 1][:cap * 2]
         self.closed_cap = cap
 
     def _fill_ctx(self) -> None:
@@ -202,21 +208,17 @@ class SearchEngine:
         self._n_kept_ptr = self.state_buf.data_ptr() + 4 * 2          # &plan.n_kept
 
     def _grow_closed(self, need_entries: int) -> None:
-        """Stream-ordered: clear a larger table, re-insert every entry (dcb_closed_rehash), switch."""
-        new_cap = self.closed_cap
-        while new_cap < self.closed_cap_max and 2 * need_entries > new_cap:
-            new_cap *= 2
-        if new_cap == self.closed_cap:
-            return
+        """Stream-ordered: clear the next larger table, re-insert every entry (dcb_closed_rehash), switch.  One doubling at a time:
+        consecutive sizes live in different buffers."""
         lib, st = self.lib, self._stream()
-        old, old_cap = self.closed, self.closed_cap
-        self._alloc_closed(new_cap)
-        check(lib.dcb_closed_clear(ptr(self.closed), new_cap, st), "closed_clear")
-        check(lib.dcb_closed_rehash(ptr(old), old_cap, ptr(self.closed), new_cap, st), "closed_rehash")
-        self.kernel_launches += 2
-        self.closed_growths += 1
+        while self.closed_cap < self.closed_cap_max and 2 * need_entries > self.closed_cap:
+            old, old_cap = self.closed, self.closed_cap
+            self._alloc_closed(2 * old_cap)
+            check(lib.dcb_closed_clear(ptr(self.closed), self.closed_cap, st), "closed_clear")
+            check(lib.dcb_closed_rehash(ptr(old), old_cap, ptr(self.closed), self.closed_cap, st), "closed_rehash")
+            self.kernel_launches += 2
+            self.closed_growths += 1
         self._fill_ctx()
-        del old
 
     # ---- device -> host ------------------------------------------------------------------------------
     def _readback(self, slot: int) -> None:

@@ -3,7 +3,7 @@
 directory travels to the GPU box with the working tree).  Data only -- no reference source is copied.
 bench.py and the GPU tests use them when present and fall back to seeded random-init weights otherwise.
 
-    python tools/fetch_assets.py [env ...]        (default: cube3)
+    python tools/fetch_assets.py [env ...]        (default: the BASELINE.json environments cube3 puzzle15 puzzle48, and lightsout7)
 """
 import os
 import shutil
@@ -27,4 +27,4 @@ def fetch(envs):
 
 
 if __name__ == "__main__":
-    fetch(sys.argv[1:] or ["cube3"])
+    fetch(sys.argv[1:] or ["cube3", "puzzle15", "puzzle48", "lightsout7"])

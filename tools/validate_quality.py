@@ -1,5 +1,5 @@
 """Solution quality on the reference's own test sets, against the reference's shipped results and the optimal lengths.
-    python tools/validate_quality.py <env> [n_states] [precision]  -> prints a table, writes gpurun_out/quality_r01_<env>_<prec>.txt
+    python tools/validate_quality.py <env> [n_states] [precision]  -> prints a table, writes gpurun_out/quality_r02_<env>_<prec>.txt
 Configs = the reference's published runs (train.sh:9 cube3: weight 0.6, batch 10000; train.sh:21 puzzle15: 0.8 / 20000;
 train.sh:57 puzzle48: 0.6 / 20000; train.sh:68 lightsout7: 0.2 / 1000).  Needs assets/saved_models/<env>/current/model_state_dict.pt (tools/fetch_assets.py <env>)."""
 import os, sys, time
@@ -50,4 +50,4 @@ lines += ["ours == reference length: %.1f%%; ours shorter %d, longer %d" % (100 
           "all %d solutions valid (replayed through dcb_next_state / dcb_is_solved)" % n]
 print("\n".join(lines))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-open(os.path.join(ROOT, "gpurun_out", "quality_r01_%s_%s.txt" % (name, prec)), "w").write("\n".join(lines) + "\n")
+open(os.path.join(ROOT, "gpurun_out", "quality_r02_%s_%s.txt" % (name, prec)), "w").write("\n".join(lines) + "\n")
