@@ -211,7 +211,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     heur, weights_src = build_heuristic(wl, dev, args.nnet_precision)
-    eng = BWASGpu(W["env"], heur, W["weight"], BATCH, max_nodes=args.max_nodes, device=dev)
+    max_nodes = args.max_nodes or ((1 << 28) if args.full else (1 << 27))
+    eng = BWASGpu(W["env"], heur, W["weight"], BATCH, max_nodes=max_nodes, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -370,12 +371,31 @@ def run_ours(args):
         per_rank = bucket
         nodes, ms = sharding.reduce_throughput(nodes, ms, dev)            # nodes SUM over ranks, device time MAX over ranks
         e_nodes, e_sec = sharding.reduce_throughput(e_nodes, e_sec, dev)
-        f_nodes, f_sec = sharding.reduce_throughput(f_nodes, f_sec, dev)
+        # whole searches differ in length from rank to rank: the job's rate is the sum of the ranks' own rates
+        f_rate = torch.tensor([f_nodes / f_sec if f_sec else 0.0, f_nodes], dtype=torch.float64, device=dev)
+        dist.all_reduce(f_rate, op=dist.ReduceOp.SUM)
+        f_nodes = float(f_rate[1].item())
+        f_sec = (f_nodes / float(f_rate[0].item())) if float(f_rate[0].item()) else 0.0
         cnt = torch.tensor([launches, solved, len_sum, h2d, d2h, kept, iters, f_solved, sum(f_lens)], dtype=torch.float64, device=dev)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         launches, solved, len_sum, h2d, d2h, kept, iters, f_solved, f_len_sum = cnt.tolist()
     else:
         f_len_sum = sum(f_lens)
+    extra = multi = None
+    arena_nodes = eng.max_nodes
+    if rank == 0 and world == 1 and not args.no_extras:
+        del eng
+        torch.cuda.empty_cache()
+        extra = {}
+        for other in ("puzzle15", "puzzle48"):
+            try:
+                extra[other] = workload_summary(other, dev, args.nnet_precision, peak, tc_sus)
+            except Exception as e:   # missing assets must never take the bench down
+                extra[other] = {"unavailable": str(e)[:160]}
+        try:
+            multi = multi_instance_summary(dev, heur)
+        except Exception as e:
+            multi = {"unavailable": str(e)[:160]}
     if rank == 0:
         cpu = None
         if not args.no_cpu_baseline:
@@ -394,7 +414,7 @@ def run_ours(args):
                            "step": "one FULL-BATCH BWAS iteration (pop 20000, expand %dx, CLOSED, heuristic on survivors, push); ramp-up "
                                    "iterations of a new search ride along (time and nodes counted, not steps); the children of a "
                                    "terminating iteration are not materialised and not counted" % A,
-                           "instances_per_gpu": len(states), "max_nodes": eng.max_nodes, "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world,
+                           "instances_per_gpu": len(states), "max_nodes": arena_nodes, "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world,
                            "l2": "working set (arena+CLOSED+OPEN) >> L2; roofline launches write 1.7 GB each",
                            "solved_in_timed_region": int(solved), "iterations_in_timed_region": int(iters),
                            "avg_children_per_step": nodes / args.steps / world, "avg_heuristic_rows_per_step": kept / args.steps / world,
@@ -409,10 +429,116 @@ def run_ours(args):
                 "gpu_launches": int(launches), "clocks": clocks,
                 "roofline": roof_dom if roof_dom is not None else roof,      # dominant kernel of the step
                 "roofline_gather": roof,                                      # BASELINE.json: "gather-kernel HBM GB/s vs roofline"
+                "other_workloads": extra,                                     # BASELINE configs[2] / [4]: whole searches on the reference's test states
+                "multi_instance": multi,                                      # AStar(states, ...) API: many instances per step in one engine
                 "cpu_baseline": cpu}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def workload_summary(wl, dev, precision, hbm_peak, tc_peak, n_states=3):
+    """BASELINE configs[2] / [4] in short: whole searches on the first states of the reference's test file (weight 0.8, batch 20000),
+    nodes/s by the reference's counting, the GEMM's algorithmic TFLOP/s inside the searches, the gather kernel at streaming size."""
+    import torch
+    from deepcubea_b200 import ops
+    from deepcubea_b200.search.bwas_gpu import BWASGpu
+    W = WORKLOADS[wl]
+    heur, src = build_heuristic(wl, dev, precision)
+    eng = BWASGpu(W["env"], heur, W["weight"], BATCH, max_nodes=1 << 26, device=dev)
+    states, desc = workload_states(wl, n_states + 1)
+    eng.solve(states[n_states], max_iters=12)                        # warm the kernels / buffers
+    torch.cuda.synchronize()
+    if hasattr(heur, "gemm_events"):
+        heur.gemm_events = []
+    kept0 = eng.total_kept
+    nodes = secs = 0.0
+    lens = []
+    for s in states[:n_states]:
+        t0 = time.perf_counter()
+        r = eng.solve(s)
+        secs += time.perf_counter() - t0
+        nodes += r.nodes_generated
+        lens.append(len(r.moves) if r.moves is not None else -1)
+    out = {"config": W["config"], "states": desc.replace("first %d" % (n_states + 1), "first %d" % n_states), "value": nodes / secs, "unit": UNIT,
+           "nodes_generated": int(nodes), "solution_lens": lens, "weights": src}
+    if hasattr(heur, "gemm_events") and heur.gemm_events:
+        t_s = sum(a.elapsed_time(b) for a, b, _ in heur.gemm_events) * 1e-3
+        ach = heur.flops_per_row * float(eng.total_kept - kept0) / t_s / 1e12
+        out["roofline"] = {"kernel": "resnet_gemm_pair_kernel", "bound": "tensor", "achieved": round(ach, 1), "peak": tc_peak, "unit": "TFLOP/s",
+                           "frac": round(ach / tc_peak, 4), "mflop_per_state": W["mflop"], "launches": len(heur.gemm_events),
+                           "share_of_search_time": round(t_s / secs, 4)}
+        heur.gemm_events = None
+    S, A = W["S"], W["A"]
+    alg = S / A + S + 1 + 8
+    n_par = 1 << 22
+    eid = eng.env
+    par = torch.from_numpy(states[:1].repeat(n_par, 0)).to(dev)
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    for a in torch.randint(0, A, (8,), generator=g, device=dev).tolist():
+        par = ops.next_state(eid, par, a)
+    ch = torch.empty((n_par, A, S), dtype=torch.uint8, device=dev)
+    times = []
+    for it in range(6):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); ops.expand(eid, par, out=ch); b.record(); torch.cuda.synchronize()
+        if it >= 2:
+            times.append(a.elapsed_time(b))
+    t = float(np.mean(times)) * 1e-3
+    out["roofline_gather"] = {"kernel": "expand_kernel<%s>" % wl, "bound": "hbm", "achieved": round(alg * n_par * A / t / 1e9, 1), "peak": hbm_peak,
+                              "unit": "GB/s", "frac": round(alg * n_par * A / t / 1e9 / hbm_peak, 4), "alg_bytes_per_child": alg,
+                              "children_per_sec": round(n_par * A / t, 1)}
+    del eng, heur, par, ch
+    torch.cuda.empty_cache()
+    return out
+
+
+def multi_instance_summary(dev, heur, n_inst=64, batch=100, weight=0.6):
+    """The reference's multi-instance API (AStar(states, env, heuristic_fn, weights); astar.py:232-317 -- what its GBFS / AVI updaters
+    drive): 64 cube3 instances, batch 100 each, advanced together by ONE engine (one pop / expand / CLOSED / network call per step)
+    against the same instances solved one after the other by a single-instance engine."""
+    import torch
+    from deepcubea_b200.search.engine import BWASGpu, SearchEngine
+    from deepcubea_b200.utils.env_utils import get_environment
+    env = get_environment("cube3")
+    np.random.seed(SEED + 1); random.seed(SEED + 1)
+    st, depths = env.generate_states(n_inst, (8, 14))
+    starts = env.pack(st)
+    eng = SearchEngine("cube3", heur, [weight] * n_inst, batch, n_inst=n_inst, max_nodes=1 << 25, device=dev, semantics="python")
+    eng.raise_on_error = False
+
+    def run_multi():
+        eng.reset(starts)
+        steps = 0
+        while eng.running() and steps < 2000:
+            eng.step_all(); steps += 1
+        return steps, sum(int(r.nodes_generated) for r in eng.inst), sum(1 for r in eng.inst if r.n_goals)
+    run_multi()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    steps, nodes, solved = run_multi()
+    torch.cuda.synchronize(); t_multi = time.perf_counter() - t0
+    del eng
+    one = BWASGpu("cube3", heur, weight, batch, max_nodes=1 << 22, device=dev, semantics="python")
+
+    def run_seq():
+        it = nd = 0
+        for s in starts:
+            one.reset(s)
+            while not one.goal_ids and not one.done and one.iterations < 2000:
+                one.step()
+            it += one.iterations; nd += one.nodes_generated
+        return it, nd
+    run_seq()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    it_seq, nodes_seq = run_seq()
+    torch.cuda.synchronize(); t_seq = time.perf_counter() - t0
+    del one
+    torch.cuda.empty_cache()
+    return {"workload": "%d cube3 instances (scramble depth 8-14), weight %.1f, batch_size %d per instance, Python AStar semantics" % (n_inst, weight, batch),
+            "one_engine": {"steps": steps, "seconds": round(t_multi, 4), "nodes_generated": nodes, "nodes_per_sec": nodes / t_multi,
+                           "heuristic_calls_per_step": 1, "instances_with_goal": solved},
+            "one_instance_at_a_time": {"iterations": it_seq, "seconds": round(t_seq, 4), "nodes_generated": nodes_seq, "nodes_per_sec": nodes_seq / t_seq},
+            "speedup": t_seq / t_multi, "same_nodes_generated": nodes == nodes_seq}
 
 
 def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
@@ -440,7 +566,7 @@ def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
         try:
             r = eng.solve(states[i])
             mine.append((i, len(r.moves) if r.moves is not None else -1, int(r.nodes_generated), time.perf_counter() - ts, int(r.iterations)))
-        except _lib.DcbError as e:
+        except _lib.DcbError as e:          # node arena full: the search is abandoned, its work still counts (time AND nodes)
             mine.append((i, -2, int(eng.nodes_generated), time.perf_counter() - ts, int(eng.iterations)))
     torch.cuda.synchronize()
     my_sec = time.perf_counter() - t0
@@ -578,7 +704,9 @@ def main():
     ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp16x3"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"],
                     help="heuristic arithmetic: fp16x3 = hand-written tcgen05, fp32-parity (max err 3e-5 vs fp64; default); fp32 = cuBLAS SGEMM")
     ap.add_argument("--no_cpu_baseline", action="store_true")
-    ap.add_argument("--max_nodes", type=int, default=1 << 27, help="node arena capacity per GPU (a cube3 search of the reference's test set needs up to 6.1e7)")
+    ap.add_argument("--no_extras", action="store_true", help="skip the puzzle15 / puzzle48 / multi-instance summaries (N=1 only)")
+    ap.add_argument("--max_nodes", type=int, default=0, help="node arena capacity per GPU (default 2^27; 2^28 with --full: at weight 0.8 / batch 20000 "
+                    "the hardest of 1000 scrambles generate more than 1.3e8 nodes; the reference's own weight-0.6 runs needed up to 6.1e7)")
     ap.add_argument("--full_states", type=int, default=2, help="whole searches per GPU run to completion after the window (full_search in the line)")
     ap.add_argument("--full", action="store_true", help="run --num_states start states per GPU to completion (BASELINE configs[1]/[3]) instead of the window")
     ap.add_argument("--num_states", type=int, default=1000)

@@ -433,27 +433,32 @@ class BWASGpu(SearchEngine):
         t_begin = time.perf_counter()
         self.reset(start)
         trace: List[Dict] = []
-        if keep_trace or max_iters is not None or not self.sync_free or self.profile:
-            while not self.done:
-                if max_iters is not None and self.iterations >= max_iters:
-                    break
-                rec = self.step(keep_trace)
-                if keep_trace:
-                    trace.append(rec)
-        else:
-            # pipelined: iteration k+1 is enqueued before the host looks at iteration k; once `done` is set on the device the
-            # speculative iteration pops nothing and costs a handful of empty launches
-            k = 0
-            self.enqueue_step(); self._readback(0)
-            while True:
-                self.enqueue_step(); self._readback((k + 1) % 2)
-                self._wait(k % 2)
-                self._after_state()
-                if self.inst[0].done:
-                    break
-                k += 1
-            self._wait((k + 1) % 2)              # drain the speculative iteration (its record equals the final one)
-            self._absorb()
+        try:
+            if keep_trace or max_iters is not None or not self.sync_free or self.profile:
+                while not self.done:
+                    if max_iters is not None and self.iterations >= max_iters:
+                        break
+                    rec = self.step(keep_trace)
+                    if keep_trace:
+                        trace.append(rec)
+            else:
+                # pipelined: iteration k+1 is enqueued before the host looks at iteration k; once `done` is set on the device the
+                # speculative iteration pops nothing and costs a handful of empty launches
+                k = 0
+                self.enqueue_step(); self._readback(0)
+                while True:
+                    self.enqueue_step(); self._readback((k + 1) % 2)
+                    self._wait(k % 2)
+                    self._after_state()
+                    if self.inst[0].done:
+                        break
+                    k += 1
+                self._wait((k + 1) % 2)              # drain the speculative iteration (its record equals the final one)
+                self._absorb()
+        except _lib.DcbError:
+            self._absorb()                           # counters of the interrupted search stay readable
+            torch.cuda.current_stream(self.dev).synchronize()
+            raise
         moves = self.path_to(self.goal_id) if self.goal_id != NONE else None
         s = self.inst[0]
         return BWASResult(moves=moves, nodes_generated=self.nodes_generated, iterations=self.iterations,

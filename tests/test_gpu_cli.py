@@ -136,3 +136,35 @@ def test_bellman_backup_matches_oracle():
         assert np.allclose(np.stack(per_state), ref)
         assert np.allclose(backup, ref.min(axis=1) * ~orc.is_solved(ost))
         assert len(exp) == 300 and len(exp[0]) == orc.num_moves
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(WEIGHTS_DIR, "model_state_dict.pt")), reason="trained weights not present (assets/)")
+def test_cli_two_ranks_shard_the_states(tmp_path, golden_dir):
+    """The CLI under torchrun, one process per GPU: start states sharded over the ranks, every rank's network and engine on ITS
+    device, rank 0 alone owns output.txt / results.pkl.  Needs two GPUs (run with `gpurun --gpus 2`)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    sys.path.insert(0, ROOT)
+    from environments.cube3 import Cube3State
+    g = np.load(golden_dir + "/optimal_cube3.npz")
+    n = 6
+    states = [Cube3State(g["states"][i].astype(np.int64)) for i in range(n)]
+    opt = np.diff(g["offsets"])[:n]
+    pickle.dump({"states": states}, open(tmp_path / "in.pkl", "wb"))
+    out = tmp_path / "res"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29531",
+           os.path.join(ROOT, "search_methods", "astar.py"), "--states", str(tmp_path / "in.pkl"), "--model", WEIGHTS_DIR, "--env", "cube3",
+           "--weight", "0.6", "--batch_size", "2000", "--results_dir", str(out), "--max_nodes", str(1 << 26)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = pickle.load(open(out / "results.pkl", "rb"))
+    from deepcubea_b200.utils.env_utils import get_environment
+    from deepcubea_b200.utils.search_utils import is_valid_soln
+    env = get_environment("cube3")
+    assert len(res["solutions"]) == n
+    for i in range(n):
+        assert is_valid_soln(states[i], res["solutions"][i], env)
+        assert opt[i] <= len(res["solutions"][i]) <= opt[i] + 4
+    text = open(out / "output.txt").read()
+    assert text.count("State: ") == n
+    assert os.path.exists(out / "output.rank1.txt")
