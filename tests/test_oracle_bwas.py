@@ -81,3 +81,31 @@ def test_oracle_python_semantics_equals_reference_astar(golden_dir):
         assert r["open_size"] == c["open_size"] and r["closed_size"] == c["closed_size"]
         r32 = bwas_python(env, np.array(c["state"], np.uint8), misplaced_heuristic(env), c["weight"], c["batch"], cost_dtype=np.float32)
         assert r32["moves"] == c["moves"] and r32["nodes_generated"] == c["nodes_generated"]     # w*g exact: fp32 == fp64
+
+
+def _inconsistent(env, amp):
+    base = misplaced_heuristic(env)
+    wj = (np.arange(env.state_dim) * 2654435761 % 1000003 + 1).astype(np.int64)
+
+    def h(states):
+        r = ((states.astype(np.int64) * wj[None]).sum(axis=1) * 2654435761 % 1000003).astype(np.float32) / np.float32(1000003.0)
+        return (base(states) * np.float32(1.5) + r * np.float32(amp)).astype(np.float32)
+    return h
+
+
+@pytest.mark.parametrize("name,back,batch,weight,amp", [("cube3", (6, 11), 200, 0.6, 4.0), ("puzzle15", (15, 40), 50, 0.8, 4.0)])
+def test_stored_node_rewrite_changes_nothing(name, back, batch, weight, amp):
+    """parallel_weighted_astar.cpp:255-257 rewrites depth / parent of the node object stored in CLOSED when its state is re-reached
+    more cheaply.  The GPU engine leaves the older node alone.  Under an inconsistent heuristic that triggers
+    hundreds of rewrites the search result is the same either way (tools/exp_stored_node_rewrite.py: 60/60 over 8,514 rewrites)."""
+    env = O.get_oracle_env(name)
+    h = _inconsistent(env, amp)
+    np.random.seed(3); random.seed(3)
+    states, _ = env.generate_states(6, back)
+    links = 0
+    for s in states:
+        a = bwas(env, s, h, weight, batch, mutate_stored=True, max_iters=150)
+        b = bwas(env, s, h, weight, batch, mutate_stored=False, max_iters=150)
+        links += a["links"]
+        assert a["moves"] == b["moves"] and a["nodes_generated"] == b["nodes_generated"] and a["iterations"] == b["iterations"]
+    assert links > 20, "the heuristic no longer provokes rewrites: the test proves nothing"

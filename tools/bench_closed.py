@@ -1,6 +1,6 @@
-"""CLOSED insert + resolve at streaming size against SURVEY 8(d)'s 44 B/child (8 B hash in + 16 B slot probe + 16 B slot write
-+ 4 B keep/slot out), CUDA events, for table sizes from L2-resident to 1 GB.  Written at the end of r01 after the GPU budget was
-spent: not yet run on a B200 (the in-loop figures in DESIGN.md come from profiles/bwas_kernels_r01_ncu.txt)."""
+"""CLOSED insert-or-improve (probe / min / resolve / fix-up launches of dcb_closed_insert) against SURVEY 8(d)'s 44 B/child (8 B hash in
++ 16 B slot probe + 16 B slot write + 4 B keep/slot out), CUDA events, (a) at streaming size for table sizes from L2-resident to
+2 GB and (b) at the A* loop's size (240k candidates, half of them duplicates of earlier batches) against the table size."""
 import json, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -26,12 +26,12 @@ m = n_par * A
 arena = torch.empty(m * S + 64, dtype=torch.uint8, device="cuda"); arena[:m * S] = ch.reshape(-1)
 hs = hs.reshape(-1).contiguous()
 gd = torch.ones(m, dtype=torch.int32, device="cuda")
-slot = torch.empty(m, dtype=torch.int32, device="cuda"); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
+slot = torch.empty(int(lib.dcb_closed_scratch_bytes(m)), dtype=torch.uint8, device="cuda"); keep = torch.empty(m, dtype=torch.uint8, device="cuda")
 counter = torch.zeros(1, dtype=torch.int32, device="cuda")
 st = torch.cuda.current_stream().cuda_stream
-print("# dcb_closed_insert (insert + resolve launches), %d cube3 children per call, fresh table each call; peak = %.1f GB/s (%s)" % (m, peak, src))
+print("# dcb_closed_insert (probe + min + resolve + fix-up launches), %d cube3 children per call, fresh table each call; peak = %.1f GB/s (%s)" % (m, peak, src))
 print("%12s %10s %10s %14s %8s %10s" % ("table slots", "table MB", "us", "GB/s (44 B)", "frac", "kept"))
-for logcap in (25, 26, 27):
+for logcap in (25, 26, 27):          # load 0.37 / 0.19 / 0.09 after the call
     cap = 1 << logcap
     table = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
     ts = []
@@ -45,4 +45,30 @@ for logcap in (25, 26, 27):
     t = float(np.median(ts)) * 1e-3
     gbs = 44.0 * m / t / 1e9
     print("%12d %10d %10.1f %14.1f %8.3f %10d" % (cap, cap * 16 >> 20, t * 1e6, gbs, gbs / peak, int(keep.sum())))
+    del table
+
+# (b) the A* loop's shape: 240k candidates per call into a table that already holds `fill` states; half of each call's candidates
+# were seen before (the CLOSED hit rate of a cube3 search is 15-60 %)
+mb = 240000
+print("# in-loop shape: %d candidates per call, ~50%% already in the table" % mb)
+print("%12s %10s %10s %10s %14s %8s" % ("table slots", "table MB", "entries", "us", "GB/s (44 B)", "frac"))
+for logcap in (21, 23, 25, 27):
+    cap = 1 << logcap
+    table = torch.empty(cap * 2, dtype=torch.int64, device="cuda")
+    _lib.check(lib.dcb_closed_clear(p(table), cap, st)); counter.zero_()
+    fill = min(cap // 4, m - 6 * mb)
+    for i0 in range(0, fill, 1 << 20):                                 # pre-fill
+        n = min(1 << 20, fill - i0)
+        _lib.check(lib.dcb_closed_insert(ENV, p(table), cap, p(arena), hs.data_ptr() + 8 * i0, gd.data_ptr() + 4 * i0, None, i0, n, p(slot), p(keep), p(counter), st))
+    ts = []
+    for it in range(8):
+        i0 = fill - mb // 2 + it * (mb // 2)                           # half old, half new
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        _lib.check(lib.dcb_closed_insert(ENV, p(table), cap, p(arena), hs.data_ptr() + 8 * i0, gd.data_ptr() + 4 * i0, None, i0, mb, p(slot), p(keep), p(counter), st))
+        b.record(); torch.cuda.synchronize()
+        if it >= 2: ts.append(a.elapsed_time(b))
+    t = float(np.median(ts)) * 1e-3
+    gbs = 44.0 * mb / t / 1e9
+    print("%12d %10d %10d %10.1f %14.1f %8.3f" % (cap, cap * 16 >> 20, int(counter.item()), t * 1e6, gbs, gbs / peak))
     del table
