@@ -225,24 +225,30 @@ def run_ours(args):
     all_states, states_desc = workload_states(wl, n_inst * world)
     states = all_states[sharding.shard_indices(len(all_states), rank, world)]
 
-    trace = os.environ.get("DCB_BENCH_TRACE") == "1"       # per-iteration wall times on stderr (debugging aid; step() ends with a sync)
+    trace = os.environ.get("DCB_BENCH_TRACE") == "1"       # per-iteration wall times on stderr (debugging aid; the host runs one iteration ahead, so a line is the wait for the record of the iteration before)
 
     def run_window(k_full, cursor):
-        """Search iterations over consecutive start states until k_full FULL-BATCH iterations were materialised.
-        Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
+        """Search iterations over consecutive start states until k_full FULL-BATCH iterations were materialised.  The host runs ONE
+        ITERATION AHEAD of the device records it reads (BWASGpu.pipelined_steps: no round trip inside the loop, as in solve());
+        the device-side budget (dcb_step_plan.budget) makes the iteration in flight after the k_full-th full one a no-op, so exactly
+        k_full steps run.  Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
         nodes = iters = solved = full = 0
         lens = []
         rows0 = eng.total_kept
+        eng.set_budget(k_full)
+        steps, seen = cursor.get("steps"), cursor.get("seen", 0)
         while full < k_full:
             if iters > 400 * max(1, k_full):
                 raise _lib.DcbError("bench window: the searches never reach full batches")
-            if cursor["fresh"]:
+            if cursor["fresh"] or steps is None:
                 eng.reset(states[cursor["i"] % len(states)]); cursor["fresh"] = False
-            before = eng.nodes_expanded
+                steps = eng.pipelined_steps()
+                seen = 0
             if trace:
                 t_it = time.perf_counter(); cap0 = eng.closed_cap
-            eng.step(); iters += 1
-            got = eng.nodes_expanded - before
+            next(steps); iters += 1
+            got = eng.nodes_expanded - seen
+            seen = eng.nodes_expanded
             if trace:
                 print("  it %3d %7.2f ms  popped %6d kept %7d  open %9d  closed 2^%d%s" % (
                     iters, (time.perf_counter() - t_it) * 1e3, eng.last_popped, eng.last_kept, int(eng.inst[0].open_size), int(np.log2(cap0)),
@@ -250,12 +256,19 @@ def run_ours(args):
             nodes += got
             if got == BATCH * A:
                 full += 1
-            if not eng.done and eng.next_slot + 2 * BATCH + 64 > eng.max_slots:
-                eng.done = 3                      # arena nearly full: move on to the next instance
+            if not eng.done and full < k_full and eng.next_slot + 3 * BATCH + 64 > eng.max_slots:
+                eng.set_budget(0)                     # arena nearly full: nothing new may start ...
+                next(steps); iters += 1               # ... but the iteration already in flight is real work: count it, then move on
+                got = eng.nodes_expanded - seen; nodes += got; full += got == BATCH * A
+                eng.set_budget(k_full - full)
+                eng.done = eng.done or 3
             if eng.done:
                 if eng.done == 1:
                     solved += 1; lens.append(len(eng.path_to(eng.goal_id)))
                 cursor["i"] += 1; cursor["fresh"] = True
+        cursor["steps"] = None if cursor["fresh"] else steps
+        cursor["seen"] = seen
+        eng.set_budget(None)
         return nodes, eng.total_kept - rows0, iters, solved, lens
 
     cursor = {"i": 0, "fresh": True}
@@ -420,8 +433,8 @@ def run_ours(args):
                            "avg_children_per_step": nodes / args.steps / world, "avg_heuristic_rows_per_step": kept / args.steps / world,
                            "mean_solution_len": (len_sum / solved) if solved else None, "per_rank": per_rank},
                 "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
-                        "note": "BWASGpu.reset(host state)/step()/path_to() wall clock, same window rule; the search never leaves HBM, only "
-                                "the start state goes in and counters/solution come out"},
+                        "note": "BWASGpu.reset(host state) / pipelined_steps() / path_to() by wall clock, same window rule; the search never "
+                                "leaves HBM: the start state goes in, one 192-byte record per iteration and the solution come out"},
                 "full_search": {"value": (f_nodes / f_sec) if f_sec else None, "unit": UNIT, "states": int(args.full_states * world), "solved": int(f_solved),
                                 "nodes_generated": int(f_nodes), "mean_solution_len": (f_len_sum / f_solved) if f_solved else None,
                                 "note": "whole searches to completion right after the window (reference counting: every generated child, "

@@ -37,7 +37,7 @@ INST_WORDS = ctypes.sizeof(SearchInst) // 4
 
 class StepPlan(ctypes.Structure):
     """dcb_step_plan (include/dcb.h), 64 bytes."""
-    _fields_ = ([(n, c_uint32) for n in ("n_tiles", "n_parents", "n_kept", "n_ambiguous", "closed_entries", "n_running", "error", "reserved0")] +
+    _fields_ = ([(n, c_uint32) for n in ("n_tiles", "n_parents", "n_kept", "n_ambiguous", "closed_entries", "n_running", "error", "budget")] +
                 [("total_kept", ctypes.c_uint64), ("total_expanded", ctypes.c_uint64), ("reserved1", ctypes.c_uint64 * 2)])
 
 

@@ -28,7 +28,7 @@ int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity,
 int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst);
 int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
-                    int64_t popped_stride, void *scratch, cudaStream_t st);
+                    int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st);
 int search_reset_device(const dcb_search_ctx &c, const uint8_t *roots, cudaStream_t st);
 int search_pop_device(const dcb_search_ctx &c, int include_solved, cudaStream_t st);
 int search_expand_device(const dcb_search_ctx &c, cudaStream_t st);
@@ -300,7 +300,7 @@ int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64
   if (stop_at_goal && !d_node_solved) return DCB_ERR_BAD_ARG;
   if (!aligned16(d_scratch)) return DCB_ERR_ALIGN;
   return open_pop_device(d_state, d_key, d_id, capacity, 1, batch, -1, stop_at_goal, 0, 0, d_node_solved, nullptr, d_popped_ids, batch, d_scratch,
-                         S(stream));
+                         nullptr, S(stream));
 }
 
 // ---- node bookkeeping --------------------------------------------------------------------------------------

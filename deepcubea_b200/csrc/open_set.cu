@@ -122,7 +122,7 @@ __device__ __forceinline__ Carve carve(const Seg &g) {
 
 // mode: 0 = C++ semantics, 1 = Python semantics (instances that found their goal rest unless include_solved), -1 = stand-alone
 // queue (dcb_open_pop: C++ goal rule when asked, never rests)
-__global__ void open_pop_begin_kernel(Seg g, int mode, int include_solved) {
+__global__ void open_pop_begin_kernel(Seg g, int mode, int include_solved, const dcb_step_plan *plan) {
   const Carve c = carve(g);
   OpenState *s = c.s;
   for (int i = threadIdx.x; i < 2 * kBins; i += blockDim.x) c.hist[i] = 0;
@@ -131,7 +131,7 @@ __global__ void open_pop_begin_kernel(Seg g, int mode, int include_solved) {
   if (threadIdx.x == 0) { c.ss->min64 = ~0ull; c.ss->max64 = 0ull; }
   if (threadIdx.x == 0) {
     // an instance rests once it is done (C++: the loop test at :169; Python: astar.py:263-265 skips instances with a goal node)
-    const bool rest = mode >= 0 && s->done != 0 && !(mode == 1 && include_solved && s->done == 1);
+    const bool rest = (mode >= 0 && s->done != 0 && !(mode == 1 && include_solved && s->done == 1)) || (plan && plan->budget == 0);
     const uint32_t n = s->open_size;
     const uint32_t b = rest ? 0u : (n < (uint32_t)g.batch ? n : (uint32_t)g.batch);
     s->resting = rest ? 1u : 0u;
@@ -467,7 +467,7 @@ int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst) {
 // Pop for n_inst instances at once.  seg_cap = OPEN entries per instance, popped ids of instance i at popped_ids + i*popped_stride.
 int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
-                    int64_t popped_stride, void *scratch, cudaStream_t st) {
+                    int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st) {
   Seg g;
   g.states = reinterpret_cast<OpenState *>(state);
   g.key = key; g.id = id;
@@ -485,7 +485,7 @@ int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, i
   int batch_blocks = (batch + 255) / 256;
   if (batch_blocks > full_blocks * 2) batch_blocks = full_blocks * 2;
   const dim3 one(1, n_inst), full(full_blocks, n_inst), bat(batch_blocks, n_inst);
-  open_pop_begin_kernel<<<one, 1024, 0, st>>>(g, mode, include_solved);
+  open_pop_begin_kernel<<<one, 1024, 0, st>>>(g, mode, include_solved, plan);
   open_hist_kernel<0><<<full, 512, 0, st>>>(g);
   open_scan_kernel<0><<<one, 1024, 0, st>>>(g);
   open_hist_kernel<1><<<full, 512, 0, st>>>(g);

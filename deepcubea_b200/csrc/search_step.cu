@@ -12,7 +12,7 @@
 namespace dcb {
 int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
-                    int64_t popped_stride, void *scratch, cudaStream_t st);
+                    int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st);
 int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst);
 int closed_insert_tiles_device(int env, const TileView &v, int64_t max_m, void *tbl, int64_t cap, const uint8_t *arena, void *scratch,
                                uint32_t *kept_ids, dcb_step_plan *plan, cudaStream_t st);
@@ -33,6 +33,7 @@ search_reset_kernel(const uint8_t *__restrict__ roots, int n_inst, int semantics
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {
     dcb_step_plan z = {};
+    z.budget = plan->budget;                              // the host's iteration budget outlives a reset
     z.n_running = (uint32_t)n_inst;
     z.n_kept = semantics == 1 ? (uint32_t)n_inst : 0u;
     z.closed_entries = semantics == 0 ? (uint32_t)n_inst : 0u;
@@ -85,7 +86,7 @@ search_reset_kernel(const uint8_t *__restrict__ roots, int n_inst, int semantics
 // instance after instance.
 __global__ void __launch_bounds__(1024)
 search_plan_kernel(dcb_search_inst *__restrict__ inst, int n_inst, uint32_t slots_per_inst, uint32_t align, uint32_t popped_stride, int num_moves,
-                   uint4 *__restrict__ tiles, dcb_step_plan *__restrict__ plan) {
+                   uint32_t batch, uint4 *__restrict__ tiles, dcb_step_plan *__restrict__ plan) {
   __shared__ uint32_t part[1024];
   __shared__ uint32_t carry, tot_parents, running, err;
   const int t = threadIdx.x;
@@ -154,6 +155,8 @@ search_plan_kernel(dcb_search_inst *__restrict__ inst, int n_inst, uint32_t slot
     plan->n_running = running;
     plan->error |= err;
     plan->total_expanded += (uint64_t)tot_parents * (uint64_t)num_moves;
+    const uint32_t bud = plan->budget;
+    if (bud != 0xFFFFFFFFu && bud > 0 && tot_parents == (uint32_t)n_inst * batch) plan->budget = bud - 1;     // a full-batch iteration
   }
 }
 
@@ -243,10 +246,10 @@ int search_reset_device(const dcb_search_ctx &c, const uint8_t *roots, cudaStrea
 int search_pop_device(const dcb_search_ctx &c, int include_solved, cudaStream_t st) {
   const int A = env_moves(c.env);
   const int rc = open_pop_device(c.d_inst, c.d_open_key, c.d_open_id, c.open_per_inst, c.n_inst, c.batch, c.semantics, c.semantics == 0 ? 1 : 0,
-                                 include_solved, A, c.d_node_solved, c.d_node_g, c.d_popped_ids, ceil32(c.batch), c.d_pop_scratch, st);
+                                 include_solved, A, c.d_node_solved, c.d_node_g, c.d_popped_ids, ceil32(c.batch), c.d_pop_scratch, c.d_plan, st);
   if (rc) return rc;
   search_plan_kernel<<<1, 1024, 0, st>>>(c.d_inst, c.n_inst, c.slots_per_inst, (uint32_t)dcb_env_slot_align(c.env), ceil32(c.batch), A,
-                                         reinterpret_cast<uint4 *>(c.d_tiles), c.d_plan);
+                                         (uint32_t)c.batch, reinterpret_cast<uint4 *>(c.d_tiles), c.d_plan);
   return dcb_check_launch();
 }
 

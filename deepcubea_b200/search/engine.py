@@ -163,6 +163,8 @@ class SearchEngine:
         self._alloc_closed(self.closed_cap_min)
         self.ctx = SearchCtx()
         self._fill_ctx()
+        self._budget_h = torch.zeros(1, dtype=i32).pin_memory()
+        self.set_budget(None)
         if sync_free is None:
             sync_free = hasattr(heuristic, "eval_nodes_dev")
         if sync_free and not hasattr(heuristic, "eval_nodes_dev"):
@@ -206,6 +208,13 @@ class SearchEngine:
         c.d_pop_scratch, c.d_closed_scratch = align16(self.pop_scratch), align16(self.closed_scratch)
         self._ctx_ref = ctypes.byref(c)
         self._n_kept_ptr = self.state_buf.data_ptr() + 4 * 2          # &plan.n_kept
+
+    def set_budget(self, full_iterations: Optional[int]) -> None:
+        """dcb_step_plan.budget: the pop stage rests once this many FULL-BATCH iterations have started (None = unlimited).  With it a
+        host that enqueues one iteration ahead (pipelined_steps) still runs exactly k full iterations: the speculative one is a no-op."""
+        self._budget_h[0] = -1 if full_iterations is None else int(full_iterations)           # -1 == 0xffffffff
+        torch.cuda.current_stream(self.dev).synchronize()                                       # the pinned word may still be in flight
+        self.state_buf[7:8].copy_(self._budget_h, non_blocking=True)
 
     def _grow_closed(self, need_entries: int) -> None:
         """Stream-ordered: clear the next larger table, re-insert every entry (dcb_closed_rehash), switch.  One doubling at a time:
@@ -428,6 +437,20 @@ class BWASGpu(SearchEngine):
         if keep_trace:
             rec = {"popped": self.popped_of(0), "kept": self.kept_list()}
         return rec
+
+    def pipelined_steps(self):
+        """Generator over the iterations of the current search without a host round trip in the loop: yields after every completed
+        iteration (attributes absorbed) while the next one is already enqueued.  Stop iterating once `done` is set (the iteration in
+        flight then pops nothing) or the budget (set_budget) has run out."""
+        k = 0
+        self.enqueue_step(); self._readback(0)
+        while True:
+            self.enqueue_step(); self._readback((k + 1) % 2)
+            self._wait(k % 2)
+            self._after_state()
+            self._absorb()
+            yield k
+            k += 1
 
     def solve(self, start: np.ndarray, max_iters: Optional[int] = None, keep_trace: bool = False) -> BWASResult:
         t_begin = time.perf_counter()

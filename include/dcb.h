@@ -227,7 +227,9 @@ typedef struct dcb_step_plan {       /* one per engine; device memory; written b
   uint32_t closed_entries;           /* occupied CLOSED slots                                                      */
   uint32_t n_running;                /* instances with done == 0 after this pop                                    */
   uint32_t error;                    /* sticky bits: 1 arena full, 2 OPEN segment full, 4 CLOSED table full        */
-  uint32_t reserved0;
+  uint32_t budget;                   /* full-batch iterations (every instance pops `batch` nodes) the pop stage may still start; the pop
+                                        rests at 0; 0xffffffff = unlimited.  Set by the host, counted down on the device, kept across
+                                        dcb_search_reset: lets a host that runs one iteration ahead stop after EXACTLY k full iterations */
   uint64_t total_kept;               /* since the last reset                                                       */
   uint64_t total_expanded;           /* children materialised since the last reset                                 */
   uint64_t reserved1[2];
