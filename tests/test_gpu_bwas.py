@@ -175,6 +175,7 @@ def test_multi_instance_engine_matches_oracle_per_instance(name, back, n_inst, b
     env = O.get_oracle_env(name)
     np.random.seed(29); random.seed(29)
     states, _ = env.generate_states(n_inst, back)
+    states[n_inst // 2] = env.goal                       # one instance starts solved: its root is popped and is the goal (0 moves)
     calls = [0]
     h_t = _torch_misplaced(env)
 
@@ -254,3 +255,30 @@ def test_engine_equals_reference_binary(name, back, batch, weight):
             assert got.iterations == ref["iterations"]
     finally:
         srv.close()
+
+
+def test_include_solved_keeps_stepping_instances_with_a_goal():
+    """AStar.step(include_solved=True) (astar.py:263-265): instances that already popped a goal node keep searching; the reported
+    goal stays the one of smallest path cost.  Without the flag they rest (their node count stops growing)."""
+    from deepcubea_b200.search.engine import SearchEngine
+    env = O.get_oracle_env("cube3")
+    np.random.seed(31); random.seed(31)
+    states, _ = env.generate_states(6, (2, 5))
+    engines = []
+    for flag in (False, True):
+        eng = SearchEngine("cube3", _torch_misplaced(env), [1.0] * 6, 8, n_inst=6, max_nodes=1 << 22, semantics="python")
+        eng.reset(states)
+        for _ in range(40):
+            eng.step_all(include_solved=flag)
+        engines.append(eng)
+    rest, cont = engines
+    for i in range(6):
+        a, b = rest.inst[i], cont.inst[i]
+        assert a.n_goals >= 1 and b.n_goals >= a.n_goals
+        assert b.nodes_generated > a.nodes_generated                     # kept expanding after its goal
+        assert b.goal_key <= a.goal_key                                   # never a worse answer
+        assert len(cont.path_to(b.goal_id)) == b.goal_key                 # unit move costs: path cost == number of moves
+        cur = states[i][None]
+        for mv in cont.path_to(b.goal_id):
+            cur = env.move(cur, mv)
+        assert env.is_solved(cur)[0]
