@@ -174,25 +174,6 @@ def build_heuristic(wl, device, precision: str):
     return DeviceHeuristic(FoldedResnet(model, mode=precision).to(device), chunk=1 << 17), src
 
 
-class InstanceQueue:
-    """Dynamic whole-instance queue across ranks: an atomic fetch-add on the job's c10d store (host side, ~0.1 ms per
-    instance, nothing on the data path).  SURVEY 8(e): load imbalance between instances is THE scaling loss."""
-
-    def __init__(self, n_items: int, world: int):
-        self.n, self.world, self.local = n_items, world, 0
-        self.store = None
-        if world > 1:
-            import torch.distributed as dist
-            self.store = dist.distributed_c10d._get_default_store()
-
-    def next(self):
-        if self.store is None:
-            i = self.local; self.local += 1
-        else:
-            i = int(self.store.add("dcb_instance_queue", 1)) - 1
-        return i if i < self.n else None
-
-
 # =====================================================================================================
 def run_ours(args):
     import torch
@@ -566,7 +547,7 @@ def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
     W = WORKLOADS[wl]
     n_total = args.num_states * world
     states, desc = workload_states(wl, n_total, full=True)
-    q = InstanceQueue(len(states), world)
+    q = sharding.InstanceQueue(len(states))
     eng.solve(states[0], max_iters=6)                 # warm the kernels / allocator on every rank
     barrier()
     t0 = time.perf_counter()

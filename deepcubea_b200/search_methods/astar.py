@@ -280,8 +280,8 @@ def bwas_python(args, env: Environment, states: List[State]):
 def bwas_cuda(args, env: Environment, states: List[State]):
     """The `--language cpp` flow of astar.py:457-568 with the child process, socket and stdout protocol
     replaced by in-process calls into the C ABI: one engine per GPU, states solved one after the other.
-    Under torchrun (one process per GPU) the start states are sharded round-robin over the ranks and rank 0
-    merges the results; nothing else crosses GPUs."""
+    Under torchrun (one process per GPU) every rank draws whole start states from a dynamic queue (a fetch-add on the job's c10d
+    store: searches differ in length by orders of magnitude) and rank 0 merges the results; nothing else crosses GPUs."""
     import torch.distributed as dist
 
     from ..search import sharding
@@ -293,10 +293,9 @@ def bwas_cuda(args, env: Environment, states: List[State]):
     heuristic_fn = _load_heuristic(args, env)
     engine = BWASGpu(args.env, heuristic_fn.device_fn, args.weight, args.batch_size, max_nodes=args.max_nodes, semantics="cpp")
     packed = env.pack(states)
-    my_idx = sharding.shard_indices(len(states), rank, world_size)
     if world_size > 1:
         local_res = []
-        for state_idx in my_idx:
+        for state_idx in sharding.InstanceQueue(len(states)):
             res = engine.solve(packed[state_idx])
             if res.moves is None:
                 raise RuntimeError("OPEN exhausted without reaching the goal for state %d" % state_idx)

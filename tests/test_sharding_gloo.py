@@ -26,7 +26,15 @@ def _worker(rank, world, port, n_items, out_q):
         sharding.completion_barrier()
         merged = sharding.gather_results(local, n_items)
         nodes, secs = sharding.reduce_throughput(sum(x[1]["nodes"] for x in local), 1.0 + rank, torch.device("cpu"))
-        out_q.put((rank, mine, merged, nodes, secs))
+        # dynamic whole-instance queue: every instance is drawn exactly once, whichever rank gets there first
+        import time
+        drawn = []
+        for i in sharding.InstanceQueue(n_items):
+            drawn.append(i)
+            time.sleep(0.002 * (rank + 1))
+        sharding.completion_barrier()
+        merged_q = sharding.gather_results([(i, i * i) for i in drawn], n_items)
+        out_q.put((rank, mine, merged, nodes, secs, drawn, merged_q))
     finally:
         dist.destroy_process_group()
 
@@ -41,8 +49,8 @@ def test_two_rank_shard_gather_reduce(n_items):
         p.start()
     got = {}
     for _ in range(2):
-        rank, mine, merged, nodes, secs = q.get(timeout=120)
-        got[rank] = (mine, merged, nodes, secs)
+        rank, mine, merged, nodes, secs, drawn, merged_q = q.get(timeout=120)
+        got[rank] = (mine, merged, nodes, secs, drawn, merged_q)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -51,6 +59,8 @@ def test_two_rank_shard_gather_reduce(n_items):
     assert got[1][1] is None                                  # only rank 0 holds the merged list
     assert [m["nodes"] for m in merged] == [1000 + i for i in range(n_items)]     # input order restored
     assert [m["moves"] for m in merged] == [[i % 12, (i * 7) % 12] for i in range(n_items)]
+    assert sorted(got[0][4] + got[1][4]) == list(range(n_items))                   # the queue hands out every instance exactly once
+    assert got[0][5] == [i * i for i in range(n_items)] and got[1][5] is None
     for r in (0, 1):
         assert got[r][2] == sum(1000 + i for i in range(n_items))                  # SUM over ranks
         assert got[r][3] == 2.0                                                     # MAX over ranks
@@ -58,6 +68,7 @@ def test_two_rank_shard_gather_reduce(n_items):
 
 def test_single_process_paths():
     assert sharding.shard_indices(5, 0, 1) == [0, 1, 2, 3, 4]
+    assert list(sharding.InstanceQueue(4)) == [0, 1, 2, 3]
     assert sharding.gather_results([(1, "b"), (0, "a")], 2) == ["a", "b"]
     assert sharding.reduce_throughput(10, 2.5, torch.device("cpu")) == (10.0, 2.5)
     with pytest.raises(ValueError):
