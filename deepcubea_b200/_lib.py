@@ -24,7 +24,7 @@ class SearchInst(ctypes.Structure):
                                          "next_slot", "base_slot", "iterations", "tile_off")] +
                 [("nodes_generated", ctypes.c_uint64), ("nodes_expanded", ctypes.c_uint64)] +
                 [(n, c_uint32) for n in ("thr_key", "thr_id", "need", "prefix", "cand_count", "n_holes", "n_surv", "take_all", "n_at_pop",
-                                         "n_take", "resting", "overflow")] + [("reserved", c_uint32 * 4)])
+                                         "n_take", "resting", "overflow", "thr_lo")] + [("reserved", c_uint32 * 3)])
 
     @property
     def size(self) -> int:          # OPEN entries (the stand-alone queue's name for it)
@@ -48,7 +48,7 @@ class SearchCtx(ctypes.Structure):
     """dcb_search_ctx (include/dcb.h): geometry + device buffers of one engine."""
     _fields_ = ([(n, c_int32) for n in ("env", "n_inst", "batch", "semantics")] +
                 [("slots_per_inst", c_uint32), ("open_per_inst", c_uint32), ("closed_capacity", c_int64)] +
-                [(n, c_void_p) for n in ("d_arena", "d_node_g", "d_node_solved", "d_slot_parent", "d_closed", "d_open_key", "d_open_id", "d_inst",
+                [(n, c_void_p) for n in ("d_arena", "d_node_g", "d_node_solved", "d_slot_parent", "d_closed", "d_open_key", "d_open_id", "d_open_key_lo", "d_inst",
                                          "d_plan", "d_weights", "d_popped_ids", "d_tiles", "d_hash", "d_kept_ids", "d_pop_scratch",
                                          "d_closed_scratch")])
 

@@ -23,10 +23,10 @@ int closed_insert_device(int env, void *tbl, int64_t cap, const uint8_t *arena, 
 int64_t closed_scratch_bytes(int64_t m);
 int closed_rehash_device(const void *old_tbl, int64_t old_cap, void *new_tbl, int64_t new_cap, cudaStream_t st);
 int open_clear_device(void *state, int n_inst, cudaStream_t st);
-int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
+int open_push_device(void *state, uint32_t *key, uint32_t *key_lo, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
                      uint32_t first_id, const uint8_t *keep, int64_t m, cudaStream_t st);
 int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst);
-int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
+int open_pop_device(void *state, uint32_t *key, uint32_t *key_lo, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
                     int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st);
 int search_reset_device(const dcb_search_ctx &c, const uint8_t *roots, cudaStream_t st);
@@ -289,7 +289,7 @@ int dcb_open_clear(dcb_open_state *d_state, void *stream) {
 int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity, const float *d_cost,
                   const uint32_t *d_ids, uint32_t first_id, const uint8_t *d_keep, int64_t m, void *stream) {
   if (m < 0 || capacity <= 0 || capacity > 0xFFFFFFFFll || (m > 0 && (!d_state || !d_key || !d_id || !d_cost))) return DCB_ERR_BAD_ARG;
-  return open_push_device(d_state, d_key, d_id, capacity, d_cost, d_ids, first_id, d_keep, m, S(stream));
+  return open_push_device(d_state, d_key, nullptr, d_id, capacity, d_cost, d_ids, first_id, d_keep, m, S(stream));
 }
 int64_t dcb_open_scratch_bytes(int64_t capacity, int64_t batch) {
   return (capacity > 0 && batch > 0) ? open_scratch_bytes(capacity, batch, 1) : DCB_ERR_BAD_ARG;
@@ -299,7 +299,7 @@ int dcb_open_pop(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64
   if (!d_state || !d_key || !d_id || !d_popped_ids || !d_scratch || batch <= 0 || capacity <= 0) return DCB_ERR_BAD_ARG;
   if (stop_at_goal && !d_node_solved) return DCB_ERR_BAD_ARG;
   if (!aligned16(d_scratch)) return DCB_ERR_ALIGN;
-  return open_pop_device(d_state, d_key, d_id, capacity, 1, batch, -1, stop_at_goal, 0, 0, d_node_solved, nullptr, d_popped_ids, batch, d_scratch,
+  return open_pop_device(d_state, d_key, nullptr, d_id, capacity, 1, batch, -1, stop_at_goal, 0, 0, d_node_solved, nullptr, d_popped_ids, batch, d_scratch,
                          nullptr, S(stream));
 }
 
@@ -338,6 +338,7 @@ static int ctx_ok(const dcb_search_ctx *c) {
   const int64_t a = kNumMoves[c->env];
   if (c->n_inst <= 0 || c->n_inst > 65535 || c->batch <= 0 || (c->semantics != 0 && c->semantics != 1)) return DCB_ERR_BAD_ARG;
   if (c->slots_per_inst < 64 || c->slots_per_inst % 32 || (int64_t)c->n_inst * c->slots_per_inst * a >= (int64_t(1) << 32)) return DCB_ERR_BAD_ARG;
+  if ((c->semantics == 1) != (c->d_open_key_lo != nullptr)) return DCB_ERR_BAD_ARG;    // 64-bit keys iff float64 costs
   if (c->open_per_inst == 0 || !pow2(c->closed_capacity) || c->closed_capacity > (int64_t(1) << 31)) return DCB_ERR_BAD_ARG;
   if (!c->d_arena || !c->d_node_g || !c->d_node_solved || !c->d_slot_parent || !c->d_closed || !c->d_open_key || !c->d_open_id || !c->d_inst ||
       !c->d_plan || !c->d_weights || !c->d_popped_ids || !c->d_tiles || !c->d_hash || !c->d_kept_ids || !c->d_pop_scratch || !c->d_closed_scratch)

@@ -18,6 +18,10 @@
 //      semantics entries behind the first solved pop go back to OPEN, exactly like the reference's `break`.
 // HBM traffic per pop: 4 passes x 4 B per open entry; per push: 8 B per entry.
 //
+// WIDE KEYS: the Python AStar adds its costs in float64 (search_methods/astar.py:196).  A 64-bit cost key is kept as two arrays,
+// key (the high word: what every streaming pass reads) and key_lo (read only for entries that tie on the high word); the composite
+// becomes (key, key_lo, id) = 96 bits.  With key_lo == NULL (the C++ program's float32 costs) the low word is 0 everywhere.
+//
 // SEGMENTED: every kernel runs with gridDim.y = number of problem instances.  Instance i owns the OPEN segment
 // key/id[i * seg_cap ...], the record states[i] and its own slice of the scratch buffer, so many A* instances are popped by
 // the same launches as one.  Nothing here needs the host: counts stay in the per-instance records.
@@ -53,7 +57,7 @@ __global__ void open_clear_kernel(OpenState *s) {
 }
 
 __global__ void __launch_bounds__(256)
-open_push_kernel(OpenState *s, uint32_t *key, uint32_t *id, uint32_t capacity, const float *cost, const uint32_t *ids,
+open_push_kernel(OpenState *s, uint32_t *key, uint32_t *key_lo, uint32_t *id, uint32_t capacity, const float *cost, const uint32_t *ids,
                  uint32_t first_id, const uint8_t *keep, int64_t m) {
   const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   const bool want = i < m && (!keep || keep[i]);
@@ -61,6 +65,7 @@ open_push_kernel(OpenState *s, uint32_t *key, uint32_t *id, uint32_t capacity, c
   if (want) {
     if (pos < capacity) {
       key[pos] = __float_as_uint(cost[i]);
+      if (key_lo) key_lo[pos] = 0u;
       id[pos] = ids ? ids[i] : first_id + (uint32_t)i;
     } else {
       s->overflow = 1;   // size keeps counting; the host raises DCB_ERR_CAPACITY
@@ -78,9 +83,12 @@ struct SortScratch {                     // lives in the pop scratch buffer
 };
 
 // where instance blockIdx.y keeps its things
+struct Pop3 { unsigned long long hl; uint32_t id, pad; };      // one popped entry: (key << 32 | key_lo, id)
+__device__ __forceinline__ bool pop3_less(const Pop3 &a, const Pop3 &b) { return a.hl < b.hl || (a.hl == b.hl && a.id < b.id); }
+
 struct Seg {
   OpenState *states;
-  uint32_t *key, *id;
+  uint32_t *key, *key_lo, *id;   // key_lo may be NULL (narrow keys)
   uint64_t seg_cap;              // OPEN entries per instance
   uint8_t *scratch;
   uint64_t scratch_stride;       // bytes of pop scratch per instance
@@ -90,30 +98,36 @@ struct Seg {
 };
 struct Carve {                   // one instance's view
   OpenState *s;
-  uint32_t *key, *id;
+  uint32_t *key, *key_lo, *id;
   uint32_t *hist;
   SortScratch *ss;
-  unsigned long long *cand, *popped, *sorted, *tmp;
+  unsigned long long *cand;      // boundary-bucket candidates: (key << 32 | key_lo) ...
+  uint32_t *cand_id;             // ... and their ids
+  Pop3 *popped, *sorted, *tmp;
   uint32_t *holes, *surv, *popped_ids;
 };
 __host__ __device__ inline uint64_t sort_scratch_bytes() { return (sizeof(SortScratch) + 15) / 16 * 16; }
-// per-instance scratch layout (bytes): hist 2*4096*4 | sort scratch | cand 8*cap | popped 8*batch | sorted 8*batch | tmp 8*batch | holes 4*batch | surv 4*batch
+// per-instance scratch layout (bytes): hist 2*4096*4 | sort scratch | cand 8*cap | cand_id 4*cap | popped 16*batch | sorted 16*batch | tmp 16*batch
+// | holes 4*batch | surv 4*batch
 __host__ __device__ inline uint64_t pop_scratch_stride(uint64_t seg_cap, uint64_t batch) {
-  return (2 * kBins * 4 + sort_scratch_bytes() + 8 * seg_cap + 32 * batch + 255) / 256 * 256;
+  return (2 * kBins * 4 + sort_scratch_bytes() + 12 * ((seg_cap + 3) / 4 * 4) + 56 * batch + 255) / 256 * 256;
 }
 __device__ __forceinline__ Carve carve(const Seg &g) {
   const uint32_t inst = blockIdx.y;
   Carve c;
   c.s = g.states + inst;
   c.key = g.key + inst * g.seg_cap;
+  c.key_lo = g.key_lo ? g.key_lo + inst * g.seg_cap : nullptr;
   c.id = g.id + inst * g.seg_cap;
+  const uint64_t cap4 = (g.seg_cap + 3) / 4 * 4;
   uint8_t *p = g.scratch + inst * g.scratch_stride;
   c.hist = reinterpret_cast<uint32_t *>(p); p += 2 * kBins * 4;
   c.ss = reinterpret_cast<SortScratch *>(p); p += sort_scratch_bytes();
-  c.cand = reinterpret_cast<unsigned long long *>(p); p += 8 * g.seg_cap;
-  c.popped = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
-  c.sorted = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
-  c.tmp = reinterpret_cast<unsigned long long *>(p); p += 8 * (uint64_t)g.batch;
+  c.cand = reinterpret_cast<unsigned long long *>(p); p += 8 * cap4;
+  c.cand_id = reinterpret_cast<uint32_t *>(p); p += 4 * cap4;
+  c.popped = reinterpret_cast<Pop3 *>(p); p += 16 * (uint64_t)g.batch;
+  c.sorted = reinterpret_cast<Pop3 *>(p); p += 16 * (uint64_t)g.batch;
+  c.tmp = reinterpret_cast<Pop3 *>(p); p += 16 * (uint64_t)g.batch;
   c.holes = reinterpret_cast<uint32_t *>(p); p += 4 * (uint64_t)g.batch;
   c.surv = reinterpret_cast<uint32_t *>(p);
   c.popped_ids = g.popped_ids + (uint64_t)inst * g.popped_stride;
@@ -146,6 +160,7 @@ __global__ void open_pop_begin_kernel(Seg g, int mode, int include_solved, const
     s->n_popped = 0;
     s->n_expand = 0;
     s->thr_key = kNone;
+    s->thr_lo = kNone;
     s->thr_id = kNone;
   }
 }
@@ -219,30 +234,38 @@ __global__ void __launch_bounds__(512) open_collect_kernel(Seg g) {
     const uint32_t i = i0 + threadIdx.x;
     const bool hit = i < n && (key[i] >> 8) == prefix;
     const uint32_t pos = warp_agg_inc(&s->cand_count, hit);
-    if (hit) c.cand[pos] = ((unsigned long long)key[i] << 32) | id[i];
+    if (hit) {
+      c.cand[pos] = ((unsigned long long)key[i] << 32) | (c.key_lo ? c.key_lo[i] : 0u);
+      c.cand_id[pos] = id[i];
+    }
   }
 }
 
-// Single block: the `need`-th smallest of the candidates, by 8-bit radix passes over their low 40 bits.
+// Single block: the `need`-th smallest of the candidates, by 8-bit radix passes over the 72 bits still open: the low 8 bits of the
+// key, key_lo, id (the top 24 key bits are the bucket prefix).  A candidate is the 96-bit value (key, key_lo, id).
 __global__ void __launch_bounds__(1024) open_select_finish_kernel(Seg g) {
   const Carve c = carve(g);
   OpenState *s = c.s;
   if (s->take_all) return;
   __shared__ uint32_t hist[256];
-  __shared__ unsigned long long sel_prefix;
+  __shared__ unsigned __int128 sel_prefix;
   __shared__ uint32_t sel_need;
   const uint32_t nc = s->cand_count;
   const unsigned long long *cand = c.cand;
-  if (threadIdx.x == 0) { sel_prefix = (unsigned long long)s->prefix; sel_need = s->need; }   // 24 bits known
+  const uint32_t *cand_id = c.cand_id;
+  const int n_pass = c.key_lo ? 9 : 5;               // narrow keys: key_lo is 0 everywhere, its four digits need no pass
+  if (threadIdx.x == 0) { sel_prefix = (unsigned __int128)s->prefix; sel_need = s->need; }   // 24 bits known
   __syncthreads();
-  for (int pass = 0; pass < 5; pass++) {
-    const int shift = 32 - 8 * pass;            // digit = bits [shift+7 .. shift] of the 64-bit composite
+  for (int pass = 0; pass < n_pass; pass++) {
+    // digit positions inside the 96-bit value: pass 0 = bits 71..64; then (wide) 63..32 key_lo; then 31..0 id
+    const int shift = c.key_lo ? 64 - 8 * pass : (pass == 0 ? 64 : 32 - 8 * pass);
     if (threadIdx.x < 256) hist[threadIdx.x] = 0;
     __syncthreads();
-    const unsigned long long pre = sel_prefix;
+    const unsigned __int128 pre = sel_prefix;
+    const int pre_shift = (!c.key_lo && pass == 1) ? 64 : shift + 8;      // narrow: skip over the (all-zero) key_lo digits
     for (uint32_t i = threadIdx.x; i < nc; i += blockDim.x) {
-      const unsigned long long v = cand[i];
-      if ((v >> (shift + 8)) == pre) atomicAdd(&hist[(uint32_t)(v >> shift) & 0xFF], 1u);
+      const unsigned __int128 v = ((unsigned __int128)cand[i] << 32) | cand_id[i];
+      if ((v >> pre_shift) == pre) atomicAdd(&hist[(uint32_t)(v >> shift) & 0xFF], 1u);
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -252,14 +275,18 @@ __global__ void __launch_bounds__(1024) open_select_finish_kernel(Seg g) {
         if (below + hist[b] >= need) break;
         below += hist[b];
       }
-      sel_prefix = (pre << 8) | (unsigned long long)b;
+      unsigned __int128 p2 = pre;
+      if (!c.key_lo && pass == 1) p2 <<= 32;                                // the key_lo digits of a narrow key: zeros
+      sel_prefix = (p2 << 8) | (unsigned __int128)b;
       sel_need = need - below;
     }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    s->thr_key = (uint32_t)(sel_prefix >> 32);
-    s->thr_id = (uint32_t)sel_prefix;
+    const unsigned __int128 t = sel_prefix;          // the full 96-bit threshold
+    s->thr_key = (uint32_t)(t >> 64);
+    s->thr_lo = (uint32_t)(t >> 32);
+    s->thr_id = (uint32_t)t;
   }
 }
 
@@ -271,27 +298,29 @@ __global__ void __launch_bounds__(512) open_partition_kernel(Seg g) {
   if (b == 0) return;
   const uint32_t n = s->n_at_pop;
   const uint32_t new_size = n - b;
-  const uint32_t tk = s->thr_key, ti = s->thr_id;
+  const uint32_t tk = s->thr_key, tl = s->thr_lo, ti = s->thr_id;
   const uint32_t *__restrict__ key = c.key, *__restrict__ id = c.id;
   for (uint32_t i0 = blockIdx.x * blockDim.x; i0 < n; i0 += gridDim.x * blockDim.x) {
     const uint32_t i = i0 + threadIdx.x;
     bool pop = false, hole = false, sv = false;
-    uint32_t k = 0, d = 0;
+    uint32_t k = 0, l = 0, d = 0;
     if (i < n) {
       k = key[i];
       if (k <= tk) {
         d = id[i];
-        pop = (k < tk) || (d <= ti);
+        l = c.key_lo ? c.key_lo[i] : 0u;
+        pop = (k < tk) || (l < tl) || (l == tl && d <= ti);
       }
       hole = pop && i < new_size;
       sv = !pop && i >= new_size;
     }
     const uint32_t pp = warp_agg_inc(&s->n_popped, pop);
     if (pop) {
-      const unsigned long long v = ((unsigned long long)k << 32) | d;
+      Pop3 v;
+      v.hl = ((unsigned long long)k << 32) | l; v.id = d; v.pad = 0;
       c.popped[pp] = v;
-      atomicMin(&c.ss->min64, v);
-      atomicMax(&c.ss->max64, v);
+      atomicMin(&c.ss->min64, v.hl);
+      atomicMax(&c.ss->max64, v.hl);
     }
     const uint32_t hp = warp_agg_inc(&s->n_holes, hole);
     if (hole) c.holes[hp] = i;
@@ -305,13 +334,14 @@ __global__ void __launch_bounds__(256) open_fill_holes_kernel(Seg g) {
   const uint32_t cnt = c.s->n_holes;   // == n_surv
   for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < cnt; j += gridDim.x * blockDim.x) {
     c.key[c.holes[j]] = c.key[c.surv[j]];
+    if (c.key_lo) c.key_lo[c.holes[j]] = c.key_lo[c.surv[j]];
     c.id[c.holes[j]] = c.id[c.surv[j]];
   }
 }
 
-// Sorting the popped composites (all distinct) into cost order = the reference's pop order.  Bucket by a monotone map of
-// the value onto kSortBins equal slices of [min, threshold], counting-sort into bucket order, then rank only within a
-// bucket (a handful of elements): O(b) instead of the O(b^2) plain rank sort (175 us at b = 20000).
+// Sorting the popped entries (all distinct) into cost order = the reference's pop order.  Bucket by a monotone map of the 64-bit
+// key onto kSortBins equal slices of [min, max], counting-sort into bucket order, then rank only within a bucket (a handful of
+// elements, compared as (key, key_lo, id)): O(b) instead of the O(b^2) plain rank sort (175 us at b = 20000).
 __device__ __forceinline__ uint32_t sort_bucket(unsigned long long v, unsigned long long lo, double scale) {
   const double x = (double)(v - lo) * scale;                  // monotone in v
   const uint32_t b = (uint32_t)x;
@@ -325,7 +355,7 @@ __global__ void __launch_bounds__(256) open_sort_count_kernel(Seg g) {
   const Carve c = carve(g);
   const uint32_t b = c.s->n_popped;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x)
-    atomicAdd(&c.ss->counts[sort_bucket(c.popped[i], c.ss->min64, sort_scale(c.ss))], 1u);
+    atomicAdd(&c.ss->counts[sort_bucket(c.popped[i].hl, c.ss->min64, sort_scale(c.ss))], 1u);
 }
 __global__ void __launch_bounds__(1024) open_sort_scan_kernel(Seg g) {      // exclusive scan of kSortBins counts
   const Carve c = carve(g);
@@ -353,8 +383,8 @@ __global__ void __launch_bounds__(256) open_sort_scatter_kernel(Seg g) {
   const Carve c = carve(g);
   const uint32_t b = c.s->n_popped;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
-    const unsigned long long v = c.popped[i];
-    const uint32_t k = sort_bucket(v, c.ss->min64, sort_scale(c.ss));
+    const Pop3 v = c.popped[i];
+    const uint32_t k = sort_bucket(v.hl, c.ss->min64, sort_scale(c.ss));
     c.tmp[c.ss->counts[k] + atomicAdd(&c.ss->cursor[k], 1u)] = v;
   }
 }
@@ -362,11 +392,11 @@ __global__ void __launch_bounds__(256) open_sort_rank_kernel(Seg g) {
   const Carve c = carve(g);
   const uint32_t b = c.s->n_popped;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < b; i += gridDim.x * blockDim.x) {
-    const unsigned long long v = c.tmp[i];
-    const uint32_t k = sort_bucket(v, c.ss->min64, sort_scale(c.ss));
+    const Pop3 v = c.tmp[i];
+    const uint32_t k = sort_bucket(v.hl, c.ss->min64, sort_scale(c.ss));
     const uint32_t lo = c.ss->counts[k], hi = c.ss->counts[k + 1];
     uint32_t rank = lo;
-    for (uint32_t j = lo; j < hi; j++) rank += c.tmp[j] < v;
+    for (uint32_t j = lo; j < hi; j++) rank += pop3_less(c.tmp[j], v);
     c.sorted[rank] = v;
   }
 }
@@ -388,17 +418,17 @@ open_finalize_kernel(Seg g, int mode, int stop_at_goal, int num_moves, const uin
   const uint32_t b = s->n_popped;
   const uint32_t n = s->n_at_pop;
   const uint32_t new_size = n - b;
-  const unsigned long long *__restrict__ sorted = c.sorted;
+  const Pop3 *__restrict__ sorted = c.sorted;
   if (threadIdx.x == 0) { first_solved = kNone; best_goal = ~0ull; goals_here = 0; }
   __syncthreads();
   if (mode <= 0 && stop_at_goal && node_solved) {
     uint32_t best = kNone;
     for (uint32_t j = threadIdx.x; j < b; j += blockDim.x)
-      if (node_solved[(uint32_t)sorted[j]]) { best = j; break; }   // j ascending per thread
+      if (node_solved[sorted[j].id]) { best = j; break; }   // j ascending per thread
     if (best != kNone) atomicMin(&first_solved, best);
   } else if (mode == 1) {
     for (uint32_t j = threadIdx.x; j < b; j += blockDim.x) {
-      const uint32_t nid = (uint32_t)sorted[j];
+      const uint32_t nid = sorted[j].id;
       if (node_solved[nid]) {
         atomicAdd(&goals_here, 1u);
         atomicMin(&best_goal, ((unsigned long long)node_g[nid] << 32) | j);
@@ -409,27 +439,28 @@ open_finalize_kernel(Seg g, int mode, int stop_at_goal, int num_moves, const uin
   const uint32_t fs = first_solved;
   const uint32_t m = (fs != kNone) ? fs + 1 : b;                    // pops that stand
   for (uint32_t j = threadIdx.x; j < b; j += blockDim.x) {
-    const unsigned long long v = sorted[j];
-    if (j < m) c.popped_ids[j] = (uint32_t)v;
+    const Pop3 v = sorted[j];
+    if (j < m) c.popped_ids[j] = v.id;
     else {                                                         // back to OPEN
-      c.key[new_size + (j - m)] = (uint32_t)(v >> 32);
-      c.id[new_size + (j - m)] = (uint32_t)v;
+      c.key[new_size + (j - m)] = (uint32_t)(v.hl >> 32);
+      if (c.key_lo) c.key_lo[new_size + (j - m)] = (uint32_t)v.hl;
+      c.id[new_size + (j - m)] = v.id;
     }
   }
   if (threadIdx.x == 0) {
     uint32_t done = s->done;
-    const uint32_t min_key = b ? (uint32_t)(sorted[0] >> 32) : kNone;
+    const uint32_t min_key = b ? (uint32_t)(sorted[0].hl >> 32) : kNone;
     if (mode <= 0) {
       const bool goal_prev = s->goal_id != kNone;
       if (fs != kNone) {
-        const uint32_t gk = (uint32_t)(sorted[fs] >> 32), gi = (uint32_t)sorted[fs];
+        const uint32_t gk = (uint32_t)(sorted[fs].hl >> 32), gi = sorted[fs].id;
         if (g.batch == 1) { s->goal_id = gi; s->goal_key = gk; done = 1; }            // :191-193
         else if (!goal_prev || s->goal_key > gk) { s->goal_id = gi; s->goal_key = gk; }  // :195-199
       }
       if (stop_at_goal && goal_prev && b && min_key >= s->goal_key) done = 1;         // :205-208
     } else if (goals_here) {
       const uint32_t gg = (uint32_t)(best_goal >> 32), pos = (uint32_t)best_goal;
-      if (s->goal_id == kNone || gg < s->goal_key) { s->goal_id = (uint32_t)sorted[pos]; s->goal_key = gg; }
+      if (s->goal_id == kNone || gg < s->goal_key) { s->goal_id = sorted[pos].id; s->goal_key = gg; }
       s->n_goals += goals_here;
       done = 1;
     }
@@ -452,10 +483,10 @@ int open_clear_device(void *state, int n_inst, cudaStream_t st) {
   return dcb_check_launch();
 }
 
-int open_push_device(void *state, uint32_t *key, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
+int open_push_device(void *state, uint32_t *key, uint32_t *key_lo, uint32_t *id, int64_t capacity, const float *cost, const uint32_t *ids,
                      uint32_t first_id, const uint8_t *keep, int64_t m, cudaStream_t st) {
   if (m == 0) return DCB_OK;
-  open_push_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<OpenState *>(state), key, id, (uint32_t)capacity, cost,
+  open_push_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(reinterpret_cast<OpenState *>(state), key, key_lo, id, (uint32_t)capacity, cost,
                                                                ids, first_id, keep, m);
   return dcb_check_launch();
 }
@@ -465,12 +496,12 @@ int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst) {
 }
 
 // Pop for n_inst instances at once.  seg_cap = OPEN entries per instance, popped ids of instance i at popped_ids + i*popped_stride.
-int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
+int open_pop_device(void *state, uint32_t *key, uint32_t *key_lo, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
                     int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st) {
   Seg g;
   g.states = reinterpret_cast<OpenState *>(state);
-  g.key = key; g.id = id;
+  g.key = key; g.key_lo = key_lo; g.id = id;
   g.seg_cap = (uint64_t)seg_cap;
   g.scratch = reinterpret_cast<uint8_t *>(scratch);
   g.scratch_stride = pop_scratch_stride((uint64_t)seg_cap, (uint64_t)batch);

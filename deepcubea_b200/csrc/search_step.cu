@@ -10,7 +10,7 @@
 #include "state_ops.cuh"
 
 namespace dcb {
-int open_pop_device(void *state, uint32_t *key, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
+int open_pop_device(void *state, uint32_t *key, uint32_t *key_lo, uint32_t *id, int64_t seg_cap, int n_inst, int32_t batch, int mode, int stop_at_goal,
                     int include_solved, int num_moves, const uint8_t *node_solved, const uint32_t *node_g, uint32_t *popped_ids,
                     int64_t popped_stride, void *scratch, const dcb_step_plan *plan, cudaStream_t st);
 int64_t open_scratch_bytes(int64_t capacity, int64_t batch, int64_t n_inst);
@@ -161,14 +161,16 @@ search_plan_kernel(dcb_search_inst *__restrict__ inst, int n_inst, uint32_t slot
 }
 
 // ---- cost + push -----------------------------------------------------------------------------------------
-// cost = h * (!solved) + weight * depth in float32, no FMA contraction (parallel_weighted_astar.cpp:298; g++ -O3 without -march
-// emits separate mulss/addss); h is clipped at 0 first (nnet_utils.py:193-194).  The node goes to the OPEN segment of the
-// instance that owns it (astar.py:206-209 add_to_open per instance).
+// C++ semantics: cost = h * (!solved) + weight * depth in float32, no FMA contraction (parallel_weighted_astar.cpp:298; g++ -O3
+// without -march emits separate mulss/addss).  Python semantics: cost = weight * path_cost + h * (!solved) in float64 with h the
+// float32 network output widened (astar.py:196; nnet_utils.py:172-194), kept as a 64-bit order-preserving key in two words.  h is
+// clipped at 0 first (nnet_utils.py:193-194).  The node goes to the OPEN segment of the instance that owns it (astar.py:206-209).
 __global__ void __launch_bounds__(256)
 search_push_kernel(const uint32_t *__restrict__ kept_ids, dcb_step_plan *__restrict__ plan, const float *__restrict__ h,
                    const float *__restrict__ dot_partial, int n_parts, float dot_bias, const uint32_t *__restrict__ node_g,
-                   const uint8_t *__restrict__ node_solved, const float *__restrict__ weights, uint32_t nodes_per_inst, int n_inst,
-                   uint32_t open_per_inst, dcb_search_inst *__restrict__ inst, uint32_t *__restrict__ open_key, uint32_t *__restrict__ open_id) {
+                   const uint8_t *__restrict__ node_solved, const double *__restrict__ weights, uint32_t nodes_per_inst, int n_inst,
+                   uint32_t open_per_inst, dcb_search_inst *__restrict__ inst, uint32_t *__restrict__ open_key,
+                   uint32_t *__restrict__ open_key_lo, uint32_t *__restrict__ open_id) {
   const uint32_t n = plan->n_kept;
   if (blockIdx.x == 0 && threadIdx.x == 0) plan->total_kept += n;
   for (uint32_t j0 = blockIdx.x * blockDim.x; j0 < n; j0 += gridDim.x * blockDim.x) {
@@ -185,7 +187,14 @@ search_push_kernel(const uint32_t *__restrict__ kept_ids, dcb_step_plan *__restr
     }
     hv = fmaxf(hv, 0.0f);
     const float ns = node_solved[id] ? 0.0f : 1.0f;
-    const float cost = __fadd_rn(__fmul_rn(hv, ns), __fmul_rn(weights[ii], (float)node_g[id]));
+    uint32_t k_hi, k_lo = 0;
+    if (open_key_lo) {
+      const double c64 = __dadd_rn(__dmul_rn(weights[ii], (double)node_g[id]), __dmul_rn((double)hv, (double)ns));
+      const unsigned long long bits = (unsigned long long)__double_as_longlong(c64);      // costs are >= 0: bit order == value order
+      k_hi = (uint32_t)(bits >> 32); k_lo = (uint32_t)bits;
+    } else {
+      k_hi = __float_as_uint(__fadd_rn(__fmul_rn(hv, ns), __fmul_rn((float)weights[ii], (float)node_g[id])));
+    }
     // one atomic per (warp, instance)
     const unsigned peers = __match_any_sync(__activemask(), ii);
     const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
@@ -194,7 +203,8 @@ search_push_kernel(const uint32_t *__restrict__ kept_ids, dcb_step_plan *__restr
     base = __shfl_sync(peers, base, leader);
     const uint32_t pos = base + __popc(peers & ((1u << lane) - 1));
     if (pos < open_per_inst) {
-      open_key[(size_t)ii * open_per_inst + pos] = __float_as_uint(cost);
+      open_key[(size_t)ii * open_per_inst + pos] = k_hi;
+      if (open_key_lo) open_key_lo[(size_t)ii * open_per_inst + pos] = k_lo;
       open_id[(size_t)ii * open_per_inst + pos] = id;
     } else {
       inst[ii].overflow = 1;
@@ -245,7 +255,7 @@ int search_reset_device(const dcb_search_ctx &c, const uint8_t *roots, cudaStrea
 
 int search_pop_device(const dcb_search_ctx &c, int include_solved, cudaStream_t st) {
   const int A = env_moves(c.env);
-  const int rc = open_pop_device(c.d_inst, c.d_open_key, c.d_open_id, c.open_per_inst, c.n_inst, c.batch, c.semantics, c.semantics == 0 ? 1 : 0,
+  const int rc = open_pop_device(c.d_inst, c.d_open_key, c.d_open_key_lo, c.d_open_id, c.open_per_inst, c.n_inst, c.batch, c.semantics, c.semantics == 0 ? 1 : 0,
                                  include_solved, A, c.d_node_solved, c.d_node_g, c.d_popped_ids, ceil32(c.batch), c.d_pop_scratch, c.d_plan, st);
   if (rc) return rc;
   search_plan_kernel<<<1, 1024, 0, st>>>(c.d_inst, c.n_inst, c.slots_per_inst, (uint32_t)dcb_env_slot_align(c.env), ceil32(c.batch), A,
@@ -273,7 +283,7 @@ int search_push_device(const dcb_search_ctx &c, const float *h, const float *dot
   if (blocks > 148 * 8) blocks = 148 * 8;
   search_push_kernel<<<(unsigned)blocks, 256, 0, st>>>(c.d_kept_ids, c.d_plan, h, dot_partial, n_parts, dot_bias, c.d_node_g, c.d_node_solved,
                                                       c.d_weights, c.slots_per_inst * (uint32_t)A, c.n_inst, c.open_per_inst, c.d_inst,
-                                                      c.d_open_key, c.d_open_id);
+                                                      c.d_open_key, c.d_open_key_lo, c.d_open_id);
   return dcb_check_launch();
 }
 

@@ -23,7 +23,8 @@ reference sends every child to the network, parallel_weighted_astar.cpp:237, the
 :285-287); children never leave the device (no socket, :121-136, 275-279); the terminating iteration's children are counted in
 `nodes_generated` (:266) but never materialised; when the stored node of a state is improved (:255-257) the reference rewrites
 its depth / parent in place, here the older node keeps its own (measured: identical solutions, tests/test_oracle_bwas.py).
-Heap ties (equal float32 cost) break towards the smaller node id = the order the nodes were pushed (heapq's FIFO, astar.py:66;
+Costs follow each semantics' own arithmetic: float32 without FMA contraction for the C++ program (:298), float64 for the Python AStar
+(astar.py:196; 64-bit keys).  Heap ties (equal cost) break towards the smaller node id = the order the nodes were pushed (heapq's FIFO, astar.py:66;
 the C++ heap's tie order is unspecified).
 
 Node ids: id = slot * A + move, state at arena + id * S.  Instance i owns slots [i * slots_per_inst, (i+1) * slots_per_inst);
@@ -134,9 +135,11 @@ class SearchEngine:
             self.slot_parent = torch.empty(I * spi + 1, dtype=i32, device=dev)
             self.open_key = torch.empty(self.max_nodes, dtype=i32, device=dev)
             self.open_id = torch.empty(self.max_nodes, dtype=i32, device=dev)
+            # Python semantics: float64 costs (astar.py:196) -> 64-bit keys, low words in a second array
+            self.open_key_lo = torch.empty(self.max_nodes, dtype=i32, device=dev) if semantics == "python" else None
             # [plan | instance records]: one device->host copy reads everything the host ever needs
             self.state_buf = torch.zeros(PLAN_WORDS + INST_WORDS * I, dtype=i32, device=dev)
-            self.weights_d = torch.tensor(ws, dtype=f32, device=dev)
+            self.weights_d = torch.tensor(ws, dtype=torch.float64, device=dev)
             self.popped_ids = torch.zeros(I * self.Bpad, dtype=i32, device=dev)
             self.tiles = torch.zeros(self.max_tiles * 4, dtype=i32, device=dev)
             self.hash_tmp = torch.empty(max(self.max_cand, 2), dtype=i64, device=dev)
@@ -200,6 +203,7 @@ class SearchEngine:
         c.slots_per_inst, c.open_per_inst, c.closed_capacity = self.slots_per_inst, self.nodes_per_inst, self.closed_cap
         c.d_arena, c.d_node_g, c.d_node_solved, c.d_slot_parent = ptr(self.arena), ptr(self.node_g), ptr(self.node_solved), ptr(self.slot_parent)
         c.d_closed, c.d_open_key, c.d_open_id = ptr(self.closed), ptr(self.open_key), ptr(self.open_id)
+        c.d_open_key_lo = ptr(self.open_key_lo)
         c.d_plan = self.state_buf.data_ptr()
         c.d_inst = self.state_buf.data_ptr() + 4 * PLAN_WORDS
         c.d_weights, c.d_popped_ids, c.d_tiles = ptr(self.weights_d), ptr(self.popped_ids), ptr(self.tiles)

@@ -164,7 +164,8 @@ typedef struct dcb_search_inst {     /* one per problem instance; lives in devic
   uint32_t thr_key, thr_id;          /* last pop: select threshold (everything <= it was removed)                  */
   uint32_t need, prefix, cand_count, n_holes, n_surv, take_all, n_at_pop, n_take, resting;   /* pop-internal     */
   uint32_t overflow;                 /* a push ran past the segment's capacity                                     */
-  uint32_t reserved[4];
+  uint32_t thr_lo;                   /* select threshold, low key word (wide keys)                                 */
+  uint32_t reserved[3];
 } dcb_search_inst;
 typedef dcb_search_inst dcb_open_state;   /* a stand-alone OPEN queue is a search instance that uses only the OPEN fields */
 int dcb_open_clear(dcb_open_state *d_state, void *stream);
@@ -173,6 +174,8 @@ int dcb_open_clear(dcb_open_state *d_state, void *stream);
 int dcb_open_push(dcb_open_state *d_state, uint32_t *d_key, uint32_t *d_id, int64_t capacity,
                   const float *d_cost, const uint32_t *d_ids, uint32_t first_id, const uint8_t *d_keep,
                   int64_t m, void *stream);
+/* (The search loop also keeps 64-bit keys -- float64 costs of the Python AStar, astar.py:196 -- as a second array of low words,
+ * dcb_search_ctx.d_open_key_lo; composite = (key, key_lo, id).  The stand-alone queue uses float32 keys.) */
 /* Remove the (up to) `batch` cheapest entries and write their node ids, in cost order, to d_popped_ids
  * [batch]; d_state->n_popped says how many.  With `stop_at_goal` the pop is truncated right after the
  * first SOLVED entry in cost order (the `break` at :190-203; the entries behind it go back to OPEN) and the
@@ -246,9 +249,12 @@ typedef struct dcb_search_ctx {      /* HOST struct: geometry + the device buffe
   uint32_t *d_slot_parent;           /* [slots] node id of the slot's parent                                       */
   void *d_closed;                    /* dcb_closed_bytes(closed_capacity)                                          */
   uint32_t *d_open_key, *d_open_id;  /* [n_inst][open_per_inst]                                                    */
+  uint32_t *d_open_key_lo;           /* [n_inst][open_per_inst] low words of 64-bit keys (semantics 1: float64 costs, astar.py:196);
+                                        NULL for semantics 0 (float32 costs, parallel_weighted_astar.cpp:298)      */
   dcb_search_inst *d_inst;           /* [n_inst]                                                                   */
   dcb_step_plan *d_plan;
-  const float *d_weights;            /* [n_inst] path-cost weight of each instance (AStar(states, env, fn, weights)) */
+  const double *d_weights;           /* [n_inst] path-cost weight of each instance (AStar(states, env, fn, weights)); semantics 0
+                                        rounds it to float32 like the C++ program's argv parsing                   */
   uint32_t *d_popped_ids;            /* [n_inst][ceil32(batch)]                                                    */
   uint32_t *d_tiles;                 /* [n_inst*ceil(batch/32)] x 4 u32                                            */
   uint64_t *d_hash;                  /* [max candidates = n_inst*ceil32(batch)*A]                                  */
@@ -270,8 +276,9 @@ int dcb_search_expand(const dcb_search_ctx *ctx, void *stream);
 /* CLOSED insert-or-improve of every candidate (dcb_closed_insert's rule, keyed per instance); survivors are appended
  * (unordered) to d_kept_ids, plan.n_kept counts them. */
 int dcb_search_closed(const dcb_search_ctx *ctx, void *stream);
-/* cost = max(h,0)*(!solved) + weight*g (dcb_compute_cost) for d_kept_ids[0..plan.n_kept) and push onto each node's instance's
- * OPEN.  The heuristic comes either as d_h [rows] or as the fused fc_out partials of dcb_resnet_gemm (d_dot_partial
+/* cost for d_kept_ids[0..plan.n_kept) and push onto each node's instance's OPEN.  Semantics 0: float32 max(h,0)*(!solved) + weight*g
+ * without FMA contraction (dcb_compute_cost; parallel_weighted_astar.cpp:298).  Semantics 1: float64 weight*g + max(h,0)*(!solved) with
+ * h the float32 network output widened (astar.py:196, nnet_utils.py:172-194), kept as a 64-bit key.  The heuristic comes either as d_h [rows] or as the fused fc_out partials of dcb_resnet_gemm (d_dot_partial
  * [rows][n_parts], summed in index order, + dot_bias). */
 int dcb_search_push(const dcb_search_ctx *ctx, const float *d_h, const float *d_dot_partial, int32_t n_parts, float dot_bias,
                     void *stream);

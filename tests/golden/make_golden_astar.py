@@ -5,7 +5,8 @@ exactly representable heuristic, produced by running the UNMODIFIED reference he
     python tests/golden/make_golden_astar.py      -> tests/golden/astar_python_traces.json
 
 Heuristic = (#positions of the nnet input that differ from the goal's) / 8 -- the same function as
-oracle.oracle_bwas.misplaced_heuristic; weights 1.0 / 0.5 keep w*g exact in float32 and float64 alike.
+oracle.oracle_bwas.misplaced_heuristic; weights 1.0 / 0.5 keep w*g exact in float32 and float64 alike, 0.8 / 0.6 do not: those
+cases pin the float64 cost arithmetic of astar.py:196.
 Shims (no source edits): np.float / np.int for numpy 2; State.__hash__ via .tobytes() (numpy 2 has no .tostring()).
 """
 import json
@@ -42,7 +43,7 @@ def main():
         np.random.seed(31); random.seed(31)
         states, _ = env.generate_states(5, back)
         attr = "colors" if env_name == "cube3" else "tiles"
-        for weight, batch in ((1.0, 1), (1.0, 10), (0.5, 100), (0.5, 7)):
+        for weight, batch in ((1.0, 1), (1.0, 10), (0.5, 100), (0.5, 7), (0.8, 10), (0.6, 100)):
             for s in states:
                 astar = AStar([s], env, heuristic_fn, [weight])
                 steps = 0

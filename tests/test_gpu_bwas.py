@@ -141,17 +141,18 @@ def test_closed_table_grows_with_the_search():
 
 @pytest.mark.parametrize("name,back,batch,weight", [("cube3", (4, 8), 10, 1.0), ("cube3", (5, 9), 100, 0.5), ("cube3", (3, 6), 1, 1.0),
                                                      ("puzzle15", (10, 24), 7, 0.5), ("puzzle48", (10, 30), 33, 1.0), ("lightsout7", (3, 5), 10, 0.5),
-                                                     ("cube4", (3, 5), 10, 1.0)])
+                                                     ("cube4", (3, 5), 10, 1.0), ("cube3", (5, 9), 50, 0.8), ("cube3", (5, 9), 20, 0.6),
+                                                     ("puzzle15", (10, 24), 30, 0.8), ("lightsout7", (3, 5), 10, 0.3)])
 def test_engine_python_semantics_matches_oracle_trace(name, back, batch, weight):
     """semantics="python" (the `AStar` class path, astar.py:232-340) trace-exact against oracle.bwas_python (itself pinned to
-    the reference's Python AStar)."""
+    the reference's Python AStar), costs in float64 like astar.py:196 (weights 0.8 / 0.6 / 0.3: w*g is not exact in float32)."""
     from deepcubea_b200.search.bwas_gpu import BWASGpu
     env = O.get_oracle_env(name)
     np.random.seed(17); random.seed(17)
     states, _ = env.generate_states(5, back)
     eng = BWASGpu(name, _torch_misplaced(env), weight, batch, max_nodes=1 << 20, semantics="python")
     for s in states:
-        ref = bwas_python(env, s, misplaced_heuristic(env), weight, batch, keep_trace=True, cost_dtype=np.float32)
+        ref = bwas_python(env, s, misplaced_heuristic(env), weight, batch, keep_trace=True)
         eng.reset(s)
         trace = []
         while not eng.goal_ids and eng.iterations < 3000:
@@ -166,7 +167,7 @@ def test_engine_python_semantics_matches_oracle_trace(name, back, batch, weight)
 
 
 @pytest.mark.parametrize("name,back,n_inst,batch,weight,sync_free", [("cube3", (3, 8), 64, 100, 0.5, False), ("cube3", (3, 8), 64, 100, 1.0, True),
-                                                                      ("puzzle15", (8, 18), 40, 20, 0.5, True), ("lightsout7", (2, 5), 9, 16, 1.0, False),
+                                                                      ("puzzle15", (8, 18), 40, 20, 0.8, True), ("lightsout7", (2, 5), 9, 16, 0.6, False),
                                                                       ("cube3", (1, 4), 1000, 4, 0.5, True)])
 def test_multi_instance_engine_matches_oracle_per_instance(name, back, n_inst, batch, weight, sync_free):
     """Many instances in ONE engine (one arena, one CLOSED keyed per instance, segmented OPEN, one heuristic call per step):
@@ -184,7 +185,7 @@ def test_multi_instance_engine_matches_oracle_per_instance(name, back, n_inst, b
         return h_t(x)
     eng = SearchEngine(name, counted, [weight] * n_inst, batch, n_inst=n_inst, max_nodes=1 << 26, semantics="python", sync_free=sync_free)
     eng.reset(states)
-    refs = [bwas_python(env, s, misplaced_heuristic(env), weight, batch, keep_trace=True, cost_dtype=np.float32) for s in states]
+    refs = [bwas_python(env, s, misplaced_heuristic(env), weight, batch, keep_trace=True) for s in states]
     A, npi = eng.A, eng.nodes_per_inst
     local = lambda ids, i: [x - i * npi for x in ids]                 # global node id -> the instance's own numbering
     steps = 0
@@ -282,3 +283,48 @@ def test_include_solved_keeps_stepping_instances_with_a_goal():
         for mv in cont.path_to(b.goal_id):
             cur = env.move(cur, mv)
         assert env.is_solved(cur)[0]
+
+
+def test_astar_class_replays_the_references_python_traces(golden_dir):
+    """The `AStar` class of this repository against traces of the REFERENCE's own Python AStar (tests/golden/astar_python_traces.json,
+    written by make_golden_astar.py running the unmodified reference): 60 cases, instances of one (env, weight, batch) group advanced
+    TOGETHER in one engine -- moves, nodes generated, steps, pops per step, OPEN size equal per instance, CLOSED size equal in total.
+    Weights 0.8 / 0.6 exercise the float64 cost keys."""
+    import json
+    from collections import defaultdict
+    from deepcubea_b200.search_methods.astar import AStar, get_path
+    from deepcubea_b200.utils.env_utils import get_environment
+    cases = json.load(open(golden_dir + "/astar_python_traces.json"))
+    groups = defaultdict(list)
+    for c in cases:
+        groups[(c["env"], c["weight"], c["batch"])].append(c)
+    assert len(cases) == 60 and len(groups) == 12
+    for (env_name, weight, batch), grp in groups.items():
+        env = get_environment(env_name)
+        goal_in = env.state_to_nnet_input(env.generate_goal_states(1))[0][0]
+
+        def fn(states, is_nnet_format=False, env=env, goal_in=goal_in):
+            x = states[0] if is_nnet_format else env.state_to_nnet_input(states)[0]
+            return (x != goal_in[None]).sum(axis=1).astype(np.float64) / 8.0
+        states = env.unpack(np.array([c["state"] for c in grp], dtype=np.uint8))
+        astar = AStar(states, env, fn, [weight] * len(grp), max_nodes=1 << 23)
+        popped_per_step = [[] for _ in grp]
+        steps = 0
+        while not min(astar.has_found_goal()):
+            before = [len(p) for p in astar.popped_ids]
+            astar.step(fn, batch)
+            steps += 1
+            for i, rec in enumerate(astar.engine.inst):
+                if not rec.resting:
+                    popped_per_step[i].append(len(astar.popped_ids[i]) - before[i])
+            assert steps < 5000
+        closed_total = 0
+        for i, c in enumerate(grp):
+            rec = astar.engine.inst[i]
+            _, soln, cost = get_path(astar.get_goal_node_smallest_path_cost(i))
+            assert [int(m) for m in soln] == c["moves"] and cost == c["path_cost"], (env_name, weight, batch, i)
+            assert rec.iterations == c["steps"] and astar.get_num_nodes_generated(i) == c["nodes_generated"]
+            assert popped_per_step[i] == c["popped_per_step"]
+            assert rec.open_size == c["open_size"]
+            closed_total += c["closed_size"]
+        assert int(astar.engine.plan.closed_entries) == closed_total

@@ -67,11 +67,12 @@ def test_min_and_sequential_dedup_agree_on_validity(name):
 
 def test_oracle_python_semantics_equals_reference_astar(golden_dir):
     """oracle.bwas_python vs traces of the reference's own Python `AStar` (tests/golden/make_golden_astar.py): same moves,
-    nodes generated, step count, pops per step, OPEN / CLOSED sizes on 40 cube3 + puzzle15 cases."""
+    nodes generated, step count, pops per step, OPEN / CLOSED sizes on 60 cube3 + puzzle15 cases; weights 0.8 / 0.6 pin the float64
+    cost arithmetic of astar.py:196."""
     import json
     from oracle.oracle_bwas import bwas_python
     cases = json.load(open(golden_dir + "/astar_python_traces.json"))
-    assert len(cases) == 40
+    assert len(cases) == 60
     for c in cases:
         env = O.get_oracle_env(c["env"])
         r = bwas_python(env, np.array(c["state"], np.uint8), misplaced_heuristic(env), c["weight"], c["batch"], batch_dedup="sequential")
@@ -79,8 +80,9 @@ def test_oracle_python_semantics_equals_reference_astar(golden_dir):
         assert r["nodes_generated"] == c["nodes_generated"] and r["steps"] == c["steps"]
         assert r["popped_per_step"] == c["popped_per_step"]
         assert r["open_size"] == c["open_size"] and r["closed_size"] == c["closed_size"]
-        r32 = bwas_python(env, np.array(c["state"], np.uint8), misplaced_heuristic(env), c["weight"], c["batch"], cost_dtype=np.float32)
-        assert r32["moves"] == c["moves"] and r32["nodes_generated"] == c["nodes_generated"]     # w*g exact: fp32 == fp64
+        if c["weight"] in (1.0, 0.5):
+            r32 = bwas_python(env, np.array(c["state"], np.uint8), misplaced_heuristic(env), c["weight"], c["batch"], cost_dtype=np.float32)
+            assert r32["moves"] == c["moves"] and r32["nodes_generated"] == c["nodes_generated"]     # w*g exact: fp32 == fp64
 
 
 def _inconsistent(env, amp):
