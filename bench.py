@@ -47,6 +47,9 @@ MIN_SCRAMBLE = 20
 SEED = 1234
 POOL = 1024                                            # size of the seeded scramble list both arms draw from
 NCU_TRAFFIC_BYTES = 116.28e6 + 1527.19e6               # ncu --set full, expand_kernel<cube3>, 2^21 parents (profiles/expand_r01_ncu.txt)
+# ncu --set full, resnet_gemm_pair_kernel, the 10 launches of one cube3 forward pass at 131072 rows (profiles/resnet_gemm_r02_ncu.txt):
+# dram__bytes_read.sum 10.72 GB + dram__bytes_write.sum 7.46 GB
+NCU_GEMM_BYTES_PER_ROW = (10.72e9 + 7.46e9) / 131072
 
 # per workload: env name, weight, state bytes, moves, MFLOP per state of the cost-to-go net, BASELINE config
 WORKLOADS = {
@@ -319,13 +322,15 @@ def run_ours(args):
         ach = fl / t_s / 1e12
         exec_ratio = (89.7 / 29.24) if args.nnet_precision == "fp16x3" else (29.9 / 29.24)
         roof_dom = {"kernel": "resnet_gemm_pair_kernel (tcgen05 cta_group::2 dense layers of the cost-to-go ResNet)", "bound": "tensor", "achieved": round(ach, 1),
-                    "peak": tc_sus, "unit": "TFLOP/s", "frac": round(ach / tc_sus, 4), "traffic": None,
+                    "peak": tc_sus, "unit": "TFLOP/s", "frac": round(ach / tc_sus, 4),
+                    "traffic": (round(NCU_GEMM_BYTES_PER_ROW * float(kept) / len(gemm_ev)) if wl == "cube3" else None),
+                    "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of the ten launches of a forward pass at 131072 rows "
+                                      "(profiles/resnet_gemm_r02_ncu.txt: 138.7 KB per row), scaled to this run's average rows per launch",
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % tc_burst,
                     "launches": len(gemm_ev), "avg_us": round(t_s / len(gemm_ev) * 1e6, 1), "share_of_timed_region": round(t_s * 1e3 / ms, 4),
                     "algorithmic_flops": "2*rows*N*K of the unpadded layer (%.2f MFLOP per %s state, SURVEY 8d), one product" % (W["mflop"], wl),
                     "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 3e-5 vs fp64) "
-                            "on padded tiles; executed tensor work ~ %.0f TFLOP/s; traffic is null because the in-loop launches differ in row "
-                            "count (per-layer DRAM bytes at 131072 rows: profiles/)" % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1", ach * exec_ratio)}
+                            "on padded tiles; executed tensor work ~ %.0f TFLOP/s" % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1", ach * exec_ratio)}
     if rank == 0 and wl == "cube3":
         alg = 54.0 / 12 + 54 + 1 + 8          # expand + is_solved + hash, unpadded
         n_par = 1 << 21

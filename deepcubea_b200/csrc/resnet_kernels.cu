@@ -542,27 +542,37 @@ __global__ void __launch_bounds__(256) onehot_kernel(const uint8_t *__restrict__
 
 // same, reading the states of the listed nodes straight from the search's node arena (state of node i at arena + i*S):
 // state_to_nnet_input (cube3.py:77-85: sticker / 9 -> colour; cube4: sticker / 16) and F.one_hot in one pass, no intermediate u8 matrix
-template <int DIV>
+// DEPTH > 0: the one-hot depth as a compile-time constant (the division k / depth becomes a multiply-shift); 0: runtime depth.
+template <int DIV, int DEPTH>
 __global__ void __launch_bounds__(256) onehot_gather_kernel(const uint8_t *__restrict__ arena, const uint32_t *__restrict__ ids, int64_t M, int S,
-                                                            int depth, int Kp, __half *__restrict__ out, const int32_t *__restrict__ m_dev, int32_t m_off) {
+                                                            int depth_rt, int Kp, __half *__restrict__ out, const int32_t *__restrict__ m_dev, int32_t m_off) {
   if (m_dev) {                                                  // device-side row count (see GemmParams::m_dev)
     const int64_t d = (int64_t)(*m_dev) - m_off;
     M = d < 0 ? 0 : (d < M ? d : M);
   }
-  const int64_t total = M * (int64_t)(Kp / 8);
+  const int depth = DEPTH > 0 ? DEPTH : depth_rt;
+  const int chunks = Kp / 8;                                    // one thread writes 8 halves (16 bytes)
+  const int64_t total = M * (int64_t)chunks;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / (Kp / 8);
-    const int k0 = (int)(i - m * (Kp / 8)) * 8;
+    const int64_t m = i / chunks;
+    const int k0 = (int)(i - m * chunks) * 8;
     const uint8_t *st = arena + (uint64_t)ids[m] * S;
-    __half h[8];
+    // the 8 columns k0..k0+7 belong to at most two positions when depth >= 8, to a handful otherwise: walk (s, v) incrementally
+    int s = k0 / depth, v = k0 - s * depth;
+    int x = -1;
+    if (s < S) { x = st[s]; if (DIV == 9) x = (x * 57) >> 9; else if (DIV == 16) x >>= 4; }
+    uint32_t w[4];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
-      const int k = k0 + e, s = k / depth, v = k - s * depth;
-      int x = -1;
-      if (s < S) { x = st[s]; if (DIV == 9) x = (x * 57) >> 9; else if (DIV == 16) x >>= 4; }
-      h[e] = (x == v) ? __float2half(1.0f) : __float2half(0.0f);
+      const uint32_t bit = (x == v) ? 0x3C00u : 0u;             // fp16 1.0
+      if (e & 1) w[e >> 1] |= bit << 16; else w[e >> 1] = bit;
+      if (++v == depth) {
+        v = 0; ++s;
+        x = -1;
+        if (s < S) { x = st[s]; if (DIV == 9) x = (x * 57) >> 9; else if (DIV == 16) x >>= 4; }
+      }
     }
-    *reinterpret_cast<uint4 *>(out + m * Kp + k0) = *reinterpret_cast<const uint4 *>(h);
+    *reinterpret_cast<uint4 *>(out + m * Kp + k0) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
@@ -693,9 +703,18 @@ int onehot_gather_device(int env, const uint8_t *arena, const uint32_t *ids, int
   if (M == 0) return DCB_OK;
   int64_t blocks = (M * (Kp / 8) + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
-  if (env == 0) onehot_gather_kernel<9><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
-  else if (env == DCB_ENV_CUBE4) onehot_gather_kernel<16><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
-  else onehot_gather_kernel<0><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off);
+#define DCB_ONEHOT(DIV, DEPTH) onehot_gather_kernel<DIV, DEPTH><<<(unsigned)blocks, 256, 0, st>>>(arena, ids, M, S, depth, Kp, (__half *)out, m_dev, m_off)
+  if (env == 0 && depth == 6) DCB_ONEHOT(9, 6);
+  else if (env == 0) DCB_ONEHOT(9, 0);
+  else if (env == DCB_ENV_CUBE4 && depth == 6) DCB_ONEHOT(16, 6);
+  else if (env == DCB_ENV_CUBE4) DCB_ONEHOT(16, 0);
+  else if (depth == 16) DCB_ONEHOT(0, 16);
+  else if (depth == 25) DCB_ONEHOT(0, 25);
+  else if (depth == 36) DCB_ONEHOT(0, 36);
+  else if (depth == 49) DCB_ONEHOT(0, 49);
+  else if (depth == 2) DCB_ONEHOT(0, 2);
+  else DCB_ONEHOT(0, 0);
+#undef DCB_ONEHOT
   return dcb_check_launch();
 }
 
