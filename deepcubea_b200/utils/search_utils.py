@@ -30,3 +30,30 @@ def bellman(states: List[State], heuristic_fn: Callable, env: Environment) -> Tu
     unsolved = np.logical_not(env.is_solved(states))
     backup = np.fromiter((row.min() for row in per_state), dtype=np.float64, count=len(per_state)) * unsolved
     return backup, per_state, children
+
+
+def bellman_packed(states, heuristic_device_fn: Callable, env: Environment):
+    """The same backup without leaving HBM and without a Python object per child -- the tensor-native form for the consumers that
+    call `bellman` on millions of states (the reference's AVI target generation, updaters/updater.py, and gbfs.py).
+
+    states: packed uint8 [n, S] (numpy or CUDA tensor).  heuristic_device_fn: nnet-input u8 [m, S] on the device -> f32 [m] on the
+    device (`heuristic_fn.device_fn` of nnet_utils.load_heuristic_fn, e.g. the tcgen05 network).
+    Returns CUDA tensors (backup f32 [n], per-action values f32 [n, A], children u8 [n, A, S], solved children u8 [n, A]).
+    One dcb_expand launch produces children + their solved flags; transition costs are 1 (cube3.py:160, n_puzzle.py:171)."""
+    import torch
+
+    from .. import ops
+    from .._lib import ENV_IDS
+    from ..search_methods.astar import _env_name
+    eid = ENV_IDS[_env_name(env)]
+    st = states if isinstance(states, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(states, dtype=np.uint8))
+    st = st.cuda().contiguous()
+    n = st.shape[0]
+    children, child_solved, _ = ops.expand(eid, st, want_hash=False)
+    a, s = children.shape[1], children.shape[2]
+    flat = children.reshape(n * a, s)
+    h = heuristic_device_fn(ops.nnet_input(eid, flat)).float().clamp_(min=0.0)      # clip_zero (nnet_utils.py:193-194)
+    per_action = 1.0 + h.reshape(n, a)
+    unsolved = ops.is_solved(eid, st) == 0
+    backup = per_action.min(dim=1).values * unsolved
+    return backup, per_action, children, child_solved

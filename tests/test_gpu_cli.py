@@ -136,6 +136,13 @@ def test_bellman_backup_matches_oracle():
         assert np.allclose(np.stack(per_state), ref)
         assert np.allclose(backup, ref.min(axis=1) * ~orc.is_solved(ost))
         assert len(exp) == 300 and len(exp[0]) == orc.num_moves
+        # the tensor-native form: same numbers, children / flags bit-exact, nothing leaves HBM until asked
+        from deepcubea_b200.utils.search_utils import bellman_packed
+        goal_in = torch.from_numpy(orc.nnet_input(orc.goal[None])[0]).cuda()
+        b2, per2, ch2, sv2 = bellman_packed(ost, lambda x: (x != goal_in[None]).sum(dim=1).float() / 8.0, env)
+        assert np.array_equal(ch2.cpu().numpy(), och)
+        assert np.array_equal(sv2.cpu().numpy().astype(bool).reshape(-1), orc.is_solved(och.reshape(-1, orc.state_dim)))
+        assert np.allclose(per2.cpu().numpy(), ref) and np.allclose(b2.cpu().numpy(), backup)
 
 
 @pytest.mark.skipif(not os.path.exists(os.path.join(WEIGHTS_DIR, "model_state_dict.pt")), reason="trained weights not present (assets/)")
