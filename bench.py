@@ -178,11 +178,119 @@ def build_heuristic(wl, device, precision: str):
 
 
 # =====================================================================================================
+class Lane:
+    """One search engine on its own CUDA stream.  A GPU runs `--lanes` of them side by side on independent problem instances:
+    the small kernels of one search (pop, expand, CLOSED, push) run while the tensor cores work on the other's network
+    (tools/exp_two_streams.py: +3 % over one search at a time).  The host enqueues iteration k+1 of a lane before it reads the
+    record of iteration k (BWASGpu.pipelined_steps)."""
+
+    def __init__(self, idx, wl, dev, precision, max_nodes, states):
+        import torch
+        from deepcubea_b200.search.bwas_gpu import BWASGpu
+        W = WORKLOADS[wl]
+        self.idx, self.A, self.states = idx, W["A"], states
+        self.heur, self.weights_src = build_heuristic(wl, dev, precision)
+        self.eng = BWASGpu(W["env"], self.heur, W["weight"], BATCH, max_nodes=max_nodes, device=dev)
+        self.stream = torch.cuda.Stream(device=dev)
+        self.i, self.gen, self.seen, self.job = 0, None, 0, None
+        self.target = self.full = self.nodes = self.iters = self.solved = 0
+        self.lens, self.rows0 = [], 0
+
+    def _ctx(self):
+        import torch
+        return torch.cuda.stream(self.stream)
+
+    # ---- window mode: consecutive start states until `k_full` FULL-BATCH iterations were materialised ---------------------
+    def begin(self, k_full):
+        with self._ctx():
+            self.eng.set_budget(k_full)       # device-side: the iteration in flight after the k_full-th full one is a no-op
+        self.target, self.full, self.nodes, self.iters, self.solved, self.lens = k_full, 0, 0, 0, 0, []
+        self.rows0 = self.eng.total_kept
+
+    def finished(self):
+        return self.full >= self.target
+
+    def advance(self):
+        from deepcubea_b200 import _lib
+        eng = self.eng
+        with self._ctx():
+            if self.iters > 400 * max(1, self.target):
+                raise _lib.DcbError("bench window: the searches never reach full batches")
+            if self.gen is None:
+                eng.reset(self.states[self.i % len(self.states)])
+                self.gen, self.seen = eng.pipelined_steps(), 0
+            next(self.gen); self.iters += 1
+            got = eng.nodes_expanded - self.seen
+            self.seen = eng.nodes_expanded
+            self.nodes += got
+            self.full += got == BATCH * self.A
+            if not eng.done and not self.finished() and eng.next_slot + 3 * BATCH + 64 > eng.max_slots:
+                eng.set_budget(0)                     # arena nearly full: nothing new may start ...
+                next(self.gen); self.iters += 1       # ... but the iteration already in flight is real work: count it, then move on
+                got = eng.nodes_expanded - self.seen; self.nodes += got; self.full += got == BATCH * self.A
+                eng.set_budget(max(self.target - self.full, 0))
+                eng.done = eng.done or 3
+            if eng.done:
+                if eng.done == 1:
+                    self.solved += 1; self.lens.append(len(eng.path_to(eng.goal_id)))
+                self.i += 1; self.gen = None
+
+    def end(self):
+        with self._ctx():
+            self.eng.set_budget(None)
+        return self.eng.total_kept - self.rows0
+
+    # ---- whole-search mode -------------------------------------------------------------------------------------------
+    def start(self, index, state):
+        with self._ctx():
+            self.eng.set_budget(None)
+            self.eng.reset(state)
+            self.gen = self.eng.pipelined_steps()
+        self.job = (index, time.perf_counter())
+
+    def poll(self):
+        """Advance the running search by one iteration; returns its result tuple once it has ended, else None."""
+        import torch
+        from deepcubea_b200 import _lib
+        eng = self.eng
+        index, t0 = self.job
+        with self._ctx():
+            try:
+                next(self.gen)
+                if not eng.done:
+                    return None
+                n_moves = len(eng.path_to(eng.goal_id)) if eng.done == 1 else -1
+            except _lib.DcbError:                 # node arena full: the search is abandoned, its work still counts (time AND nodes)
+                eng._absorb()
+                torch.cuda.current_stream().synchronize()
+                n_moves = -2
+        self.job = self.gen = None
+        return (index, n_moves, int(eng.nodes_generated), time.perf_counter() - t0, int(eng.iterations))
+
+
+def run_searches(lanes, next_index, states):
+    """Whole searches to completion, one per lane at a time, instances drawn from `next_index()` (None = exhausted)."""
+    results = []
+    while True:
+        busy = False
+        for lane in lanes:
+            if lane.job is None:
+                i = next_index()
+                if i is None:
+                    continue
+                lane.start(i, states[i])
+            busy = True
+            r = lane.poll()
+            if r is not None:
+                results.append(r)
+        if not busy:
+            return results
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
     from deepcubea_b200 import _lib, ops
-    from deepcubea_b200.search.bwas_gpu import BWASGpu
     from deepcubea_b200.search import sharding
     wl = args.workload
     W = WORKLOADS[wl]
@@ -194,130 +302,121 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    heur, weights_src = build_heuristic(wl, dev, args.nnet_precision)
     max_nodes = args.max_nodes or ((1 << 28) if args.full else (1 << 27))
-    eng = BWASGpu(W["env"], heur, W["weight"], BATCH, max_nodes=max_nodes, device=dev)
+    n_lanes = max(1, args.lanes)
 
     def barrier():
         torch.cuda.synchronize()
         sharding.completion_barrier()
 
     if args.full:
-        return run_full(args, eng, heur, rank, world, dev, weights_src, barrier)
+        lanes = [Lane(j, wl, dev, args.nnet_precision, max_nodes, None) for j in range(n_lanes)]
+        return run_full(args, lanes, rank, world, dev, barrier)
 
     n_inst = max(8, (args.steps + args.warmup) // 2)
     all_states, states_desc = workload_states(wl, n_inst * world)
     states = all_states[sharding.shard_indices(len(all_states), rank, world)]
+    lanes = [Lane(j, wl, dev, args.nnet_precision, max_nodes, states[j::n_lanes]) for j in range(n_lanes)]
+    heur, weights_src = lanes[0].heur, lanes[0].weights_src
 
-    trace = os.environ.get("DCB_BENCH_TRACE") == "1"       # per-iteration wall times on stderr (debugging aid; the host runs one iteration ahead, so a line is the wait for the record of the iteration before)
+    def run_window(k_full):
+        """k_full FULL-BATCH iterations in total, split over the lanes; the lanes are advanced in turn.
+        Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
+        for j, lane in enumerate(lanes):
+            lane.begin(k_full // n_lanes + (1 if j < k_full % n_lanes else 0))
+        while not all(l.finished() for l in lanes):
+            for lane in lanes:
+                if not lane.finished():
+                    lane.advance()
+        kept = sum(lane.end() for lane in lanes)
+        return (sum(l.nodes for l in lanes), kept, sum(l.iters for l in lanes), sum(l.solved for l in lanes), [x for l in lanes for x in l.lens])
 
-    def run_window(k_full, cursor):
-        """Search iterations over consecutive start states until k_full FULL-BATCH iterations were materialised.  The host runs ONE
-        ITERATION AHEAD of the device records it reads (BWASGpu.pipelined_steps: no round trip inside the loop, as in solve());
-        the device-side budget (dcb_step_plan.budget) makes the iteration in flight after the k_full-th full one a no-op, so exactly
-        k_full steps run.  Returns (nodes materialised, rows evaluated, iterations, solved, solution lengths)."""
-        nodes = iters = solved = full = 0
-        lens = []
-        rows0 = eng.total_kept
-        eng.set_budget(k_full)
-        steps, seen = cursor.get("steps"), cursor.get("seen", 0)
-        while full < k_full:
-            if iters > 400 * max(1, k_full):
-                raise _lib.DcbError("bench window: the searches never reach full batches")
-            if cursor["fresh"] or steps is None:
-                eng.reset(states[cursor["i"] % len(states)]); cursor["fresh"] = False
-                steps = eng.pipelined_steps()
-                seen = 0
-            if trace:
-                t_it = time.perf_counter(); cap0 = eng.closed_cap
-            next(steps); iters += 1
-            got = eng.nodes_expanded - seen
-            seen = eng.nodes_expanded
-            if trace:
-                print("  it %3d %7.2f ms  popped %6d kept %7d  open %9d  closed 2^%d%s" % (
-                    iters, (time.perf_counter() - t_it) * 1e3, eng.last_popped, eng.last_kept, int(eng.inst[0].open_size), int(np.log2(cap0)),
-                    " -> 2^%d" % int(np.log2(eng.closed_cap)) if eng.closed_cap != cap0 else ""), file=sys.stderr)
-            nodes += got
-            if got == BATCH * A:
-                full += 1
-            if not eng.done and full < k_full and eng.next_slot + 3 * BATCH + 64 > eng.max_slots:
-                eng.set_budget(0)                     # arena nearly full: nothing new may start ...
-                next(steps); iters += 1               # ... but the iteration already in flight is real work: count it, then move on
-                got = eng.nodes_expanded - seen; nodes += got; full += got == BATCH * A
-                eng.set_budget(k_full - full)
-                eng.done = eng.done or 3
-            if eng.done:
-                if eng.done == 1:
-                    solved += 1; lens.append(len(eng.path_to(eng.goal_id)))
-                cursor["i"] += 1; cursor["fresh"] = True
-        cursor["steps"] = None if cursor["fresh"] else steps
-        cursor["seen"] = seen
-        eng.set_budget(None)
-        return nodes, eng.total_kept - rows0, iters, solved, lens
-
-    cursor = {"i": 0, "fresh": True}
-    run_window(args.warmup, cursor)
+    run_window(args.warmup)
     # ---- device-resident timed region ----------------------------------------------------------------
-    eng.expand_events = []
     tc_heur = hasattr(heur, "gemm_events")
-    if tc_heur:
-        heur.gemm_events = []
-        gemm0 = heur.gemm_launches
-    launches0 = eng.kernel_launches
+    for lane in lanes:
+        lane.eng.expand_events = []
+        if tc_heur:
+            lane.heur.gemm_events = []
+    gemm0 = sum(l.heur.gemm_launches for l in lanes) if tc_heur else 0
+    launches0 = sum(l.eng.kernel_launches for l in lanes)
     sampler = ClockSampler(local); sampler.start()
     barrier()
     prof = os.environ.get("DCB_CUDA_PROFILER") == "1"     # `ncu --profile-from-start off`: capture the timed region only
     if prof:
         torch.cuda.profiler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    nodes, kept, iters, solved, lens = run_window(args.steps, cursor)
+    ev0.record()                                          # (device idle after the barrier: every lane's work starts after this point)
+    nodes, kept, iters, solved, lens = run_window(args.steps)
+    for lane in lanes:
+        torch.cuda.current_stream().wait_stream(lane.stream)
     ev1.record()
     barrier()
     if prof:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
-    launches = eng.kernel_launches - launches0
-    gemm_ev = []
+    launches = sum(l.eng.kernel_launches for l in lanes) - launches0
+    gemm_ev, gemm_busy_ms = [], 0.0
     if tc_heur:
-        gemm_ev = [(a.elapsed_time(b), f) for a, b, f in heur.gemm_events]
+        # With several lanes a GEMM launch may wait for the other lane's GEMM (both want every SM): its own event pair then spans
+        # the wait too.  The tensor cores' busy time is the UNION of the launches' [start, end] intervals on the device clock.
+        spans = sorted((ev0.elapsed_time(a), ev0.elapsed_time(b)) for l in lanes for a, b, _ in l.heur.gemm_events)
+        gemm_ev = spans
+        cur_s, cur_e = None, None
+        for a, b in spans:
+            if cur_e is None or a > cur_e:
+                gemm_busy_ms += (cur_e - cur_s) if cur_e is not None else 0.0
+                cur_s, cur_e = a, b
+            else:
+                cur_e = max(cur_e, b)
+        gemm_busy_ms += (cur_e - cur_s) if cur_e is not None else 0.0
         gemm_flops = heur.flops_per_row * float(kept)       # algorithmic: every surviving child passes through every layer once
-        heur.gemm_events = None
-        n_nn = heur.gemm_launches - gemm0
+        n_nn = sum(l.heur.gemm_launches for l in lanes) - gemm0
         launches += n_nn + max(1, n_nn // 10)              # + the one-hot kernel of each forward pass
-    in_loop = [(a.elapsed_time(b), n) for a, b, n in eng.expand_events if n]
-    eng.expand_events = None
+    for lane in lanes:
+        lane.eng.expand_events = None
+        if tc_heur:
+            lane.heur.gemm_events = None
     # ---- end-to-end through the public API: host start state in, host solution out ---------------------
-    cursor2 = {"i": cursor["i"] + 1, "fresh": True}
-    run_window(args.warmup, cursor2)                       # this search's ramp-up (untimed, as in the device window)
-    h2d0, d2h0 = eng.h2d_bytes, eng.d2h_bytes
+    for lane in lanes:                                     # fresh searches; their ramp-up is untimed, as in the device window
+        lane.i += 1 if lane.gen is not None else 0
+        lane.gen = None
+    run_window(args.warmup)
+    h2d0, d2h0 = sum(l.eng.h2d_bytes for l in lanes), sum(l.eng.d2h_bytes for l in lanes)
     barrier()
     t0 = time.perf_counter()
-    e_nodes, _, _, _, _ = run_window(args.steps, cursor2)
+    e_nodes, _, _, _, _ = run_window(args.steps)
     torch.cuda.synchronize()
     e_sec = time.perf_counter() - t0
     barrier()
-    h2d, d2h = eng.h2d_bytes - h2d0, eng.d2h_bytes - d2h0
+    h2d, d2h = sum(l.eng.h2d_bytes for l in lanes) - h2d0, sum(l.eng.d2h_bytes for l in lanes) - d2h0
+    # ---- the gather kernel at the A* loop's launch size: one lane alone, so that a launch never waits for the other lane's GEMM ----
+    one = lanes[0]
+    one.eng.expand_events = []
+    one.begin(min(10, args.steps))
+    while not one.finished():
+        one.advance()
+    one.end()
+    torch.cuda.synchronize()
+    in_loop = [(a.elapsed_time(b), n) for a, b, n in one.eng.expand_events if n and n == BATCH]
+    one.eng.expand_events = None
     # ---- whole searches to completion (steady state incl. ramp-up, large OPEN / CLOSED and the final iteration) ----------
-    f_nodes = f_sec = 0.0
-    f_solved, f_lens = 0, []
-    for j in range(args.full_states):
-        s = states[(cursor2["i"] + 1 + j) % len(states)]
-        torch.cuda.synchronize(); t0 = time.perf_counter()
-        try:
-            r = eng.solve(s)
-        except _lib.DcbError:
-            continue
-        f_sec += time.perf_counter() - t0
-        f_nodes += r.nodes_generated
-        if r.moves is not None:
-            f_solved += 1; f_lens.append(len(r.moves))
+    for lane in lanes:
+        lane.gen = None
+    todo = [(max(l.i for l in lanes) * n_lanes + n_lanes + j) % len(states) for j in range(args.full_states)]
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    res = run_searches(lanes, lambda it=iter(todo): next(it, None), states)
+    torch.cuda.synchronize()
+    f_sec = (time.perf_counter() - t0) if res else 0.0
+    f_nodes = float(sum(r[2] for r in res))
+    f_lens = [r[1] for r in res if r[1] >= 0]
+    f_solved = len(f_lens)
     # ---- rooflines ----------------------------------------------------------------------------------------------
     peak, tc_sus, tc_burst, peak_src = measured_peaks()
     roof = roof_dom = None
     if rank == 0 and gemm_ev:
-        t_s = sum(x[0] for x in gemm_ev) * 1e-3
+        t_s = gemm_busy_ms * 1e-3
         fl = gemm_flops
         ach = fl / t_s / 1e12
         exec_ratio = (89.7 / 29.24) if args.nnet_precision == "fp16x3" else (29.9 / 29.24)
@@ -328,6 +427,7 @@ def run_ours(args):
                                       "(profiles/resnet_gemm_r02_ncu.txt: 138.7 KB per row), scaled to this run's average rows per launch",
                     "peak_source": peak_src + " bf16_tflops_sustained (kernel timed inside a long step); burst %.1f" % tc_burst,
                     "launches": len(gemm_ev), "avg_us": round(t_s / len(gemm_ev) * 1e6, 1), "share_of_timed_region": round(t_s * 1e3 / ms, 4),
+                    "timing": "CUDA events around every launch on its lane's stream; busy time = union of the [start, end] intervals of all lanes",
                     "algorithmic_flops": "2*rows*N*K of the unpadded layer (%.2f MFLOP per %s state, SURVEY 8d), one product" % (W["mflop"], wl),
                     "note": "precision mode %s executes %s MMAs per algorithmic product (fp16 hi/lo operand pairs, fp32-parity: max |err| 3e-5 vs fp64) "
                             "on padded tiles; executed tensor work ~ %.0f TFLOP/s" % (args.nnet_precision, "3" if args.nnet_precision == "fp16x3" else "1", ach * exec_ratio)}
@@ -362,7 +462,7 @@ def run_ours(args):
         del par, ch
     # ---- reduce over ranks -------------------------------------------------------------------------------------
     per_rank = [{"rank": rank, "ms": round(ms, 3), "nodes": int(nodes), "heuristic_rows": int(kept), "iterations": int(iters), "solved": int(solved),
-                 "e2e_s": round(e_sec, 4), "e2e_nodes": int(e_nodes)}]
+                 "e2e_s": round(e_sec, 4), "e2e_nodes": int(e_nodes), "full_steps_per_lane": [int(l.target) for l in lanes]}]
     len_sum = sum(lens)
     if world > 1:
         bucket = [None] * world
@@ -381,9 +481,10 @@ def run_ours(args):
     else:
         f_len_sum = sum(f_lens)
     extra = multi = None
-    arena_nodes = eng.max_nodes
+    arena_nodes = lanes[0].eng.max_nodes
     if rank == 0 and world == 1 and not args.no_extras:
-        del eng
+        for lane in lanes:
+            lane.eng = None
         torch.cuda.empty_cache()
         extra = {}
         for other in ("puzzle15", "puzzle48"):
@@ -413,13 +514,16 @@ def run_ours(args):
                            "step": "one FULL-BATCH BWAS iteration (pop 20000, expand %dx, CLOSED, heuristic on survivors, push); ramp-up "
                                    "iterations of a new search ride along (time and nodes counted, not steps); the children of a "
                                    "terminating iteration are not materialised and not counted" % A,
-                           "instances_per_gpu": len(states), "max_nodes": arena_nodes, "parallelism": "instances sharded over %d GPU(s), no data-path collective" % world,
+                           "instances_per_gpu": len(states), "max_nodes": arena_nodes,
+                           "parallelism": "instances sharded over %d GPU(s), no data-path collective; %d concurrent searches (CUDA streams) per GPU: the "
+                                          "small kernels of one overlap the network of the other" % (world, n_lanes),
+                           "lanes_per_gpu": n_lanes,
                            "l2": "working set (arena+CLOSED+OPEN) >> L2; roofline launches write 1.7 GB each",
                            "solved_in_timed_region": int(solved), "iterations_in_timed_region": int(iters),
                            "avg_children_per_step": nodes / args.steps / world, "avg_heuristic_rows_per_step": kept / args.steps / world,
                            "mean_solution_len": (len_sum / solved) if solved else None, "per_rank": per_rank},
                 "e2e": {"value": e_nodes / e_sec, "unit": UNIT, "h2d_bytes_per_step": h2d / args.steps / world, "d2h_bytes_per_step": d2h / args.steps / world,
-                        "note": "BWASGpu.reset(host state) / pipelined_steps() / path_to() by wall clock, same window rule; the search never "
+                        "note": "BWASGpu.reset(host state) / pipelined_steps() / path_to() on every lane by wall clock, same window rule; the search never "
                                 "leaves HBM: the start state goes in, one 192-byte record per iteration and the solution come out"},
                 "full_search": {"value": (f_nodes / f_sec) if f_sec else None, "unit": UNIT, "states": int(args.full_states * world), "solved": int(f_solved),
                                 "nodes_generated": int(f_nodes), "mean_solution_len": (f_len_sum / f_solved) if f_solved else None,
@@ -540,33 +644,25 @@ def multi_instance_summary(dev, heur, n_inst=64, batch=100, weight=0.6):
             "speedup": t_seq / t_multi, "same_nodes_generated": nodes == nodes_seq}
 
 
-def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
+def run_full(args, lanes, rank, world, dev, barrier):
     """BASELINE configs[1] (1 GPU) / configs[3] (8 GPUs): num_states scrambles PER GPU solved to completion, whole instances
-    handed out by a dynamic queue (a rank that draws easy instances simply takes more of them).  value = sum nodes generated
+    handed out by a dynamic queue (a lane that draws easy instances simply takes more of them).  value = sum nodes generated
     (the reference's counting, scripts/compare_solutions.py:27-28) / wall time of the slowest rank."""
     import torch
     import torch.distributed as dist
-    from deepcubea_b200 import _lib
     from deepcubea_b200.search import sharding
     wl = args.workload
     W = WORKLOADS[wl]
+    weights_src = lanes[0].weights_src
     n_total = args.num_states * world
     states, desc = workload_states(wl, n_total, full=True)
     q = sharding.InstanceQueue(len(states))
-    eng.solve(states[0], max_iters=6)                 # warm the kernels / allocator on every rank
+    for lane in lanes:                                # warm the kernels / allocator on every lane of every rank
+        with lane._ctx():
+            lane.eng.solve(states[0], max_iters=6)
     barrier()
     t0 = time.perf_counter()
-    mine = []
-    while True:
-        i = q.next()
-        if i is None:
-            break
-        ts = time.perf_counter()
-        try:
-            r = eng.solve(states[i])
-            mine.append((i, len(r.moves) if r.moves is not None else -1, int(r.nodes_generated), time.perf_counter() - ts, int(r.iterations)))
-        except _lib.DcbError as e:          # node arena full: the search is abandoned, its work still counts (time AND nodes)
-            mine.append((i, -2, int(eng.nodes_generated), time.perf_counter() - ts, int(eng.iterations)))
+    mine = run_searches(lanes, q.next, states)
     torch.cuda.synchronize()
     my_sec = time.perf_counter() - t0
     barrier()
@@ -585,6 +681,7 @@ def run_full(args, eng, heur, rank, world, dev, weights_src, barrier):
                 "scaling": "weak", "data": "synthetic: " + desc + "; " + weights_src,
                 "config": {"workload": W["config"], "states": desc, "instances": len(allr), "instances_per_gpu": args.num_states,
                            "queue": "dynamic whole-instance queue (c10d store fetch-add)" if world > 1 else "in order",
+                           "lanes_per_gpu": len(lanes),
                            "per_rank": [{"rank": r, "seconds": round(s, 3), "instances": len(m), "nodes": sum(x[2] for x in m)} for r, s, m in rows]},
                 "solved": len(solved), "unsolved": len(allr) - len(solved), "nodes_generated": int(nodes), "wall_s": round(wall, 3), "max_rank_s": round(max_sec, 3),
                 "mean_solution_len": float(np.mean([x[1] for x in solved])) if solved else None,
@@ -703,6 +800,7 @@ def main():
     ap.add_argument("--nnet_precision", type=str, default=os.environ.get("DCB_NNET_PRECISION", "fp16x3"), choices=["fp32", "tf32", "bf16", "fp16x3", "fp16"],
                     help="heuristic arithmetic: fp16x3 = hand-written tcgen05, fp32-parity (max err 3e-5 vs fp64; default); fp32 = cuBLAS SGEMM")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="concurrent searches (engines on their own CUDA streams) per GPU")
     ap.add_argument("--no_extras", action="store_true", help="skip the puzzle15 / puzzle48 / multi-instance summaries (N=1 only)")
     ap.add_argument("--max_nodes", type=int, default=0, help="node arena capacity per GPU (default 2^27; 2^28 with --full: at weight 0.8 / batch 20000 "
                     "the hardest of 1000 scrambles generate more than 1.3e8 nodes; the reference's own weight-0.6 runs needed up to 6.1e7)")
