@@ -356,6 +356,7 @@ def run_ours(args):
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
+    lane_steps = [int(l.full) for l in lanes]
     launches = sum(l.eng.kernel_launches for l in lanes) - launches0
     gemm_ev, gemm_busy_ms = [], 0.0
     if tc_heur:
@@ -462,7 +463,7 @@ def run_ours(args):
         del par, ch
     # ---- reduce over ranks -------------------------------------------------------------------------------------
     per_rank = [{"rank": rank, "ms": round(ms, 3), "nodes": int(nodes), "heuristic_rows": int(kept), "iterations": int(iters), "solved": int(solved),
-                 "e2e_s": round(e_sec, 4), "e2e_nodes": int(e_nodes), "full_steps_per_lane": [int(l.target) for l in lanes]}]
+                 "e2e_s": round(e_sec, 4), "e2e_nodes": int(e_nodes), "full_steps_per_lane": lane_steps}]
     len_sum = sum(lens)
     if world > 1:
         bucket = [None] * world
