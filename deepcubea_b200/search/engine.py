@@ -186,7 +186,6 @@ class SearchEngine:
         self._phase_events = None
         self.total_kept = 0
         self._kept_base = 0                 # plan.total_kept restarts at every reset; total_kept accumulates over searches
-        self._last_total_kept = 0
 
     # ------------------------------------------------------------------------------------------------
     def _stream(self) -> int:

@@ -86,7 +86,10 @@ class AStar:
     """astar.py:232-340.  ALL instances live in one device-resident engine (search/engine.py): one node arena, one CLOSED table
     keyed per instance, segmented OPEN; a `step` pops every unsolved instance, expands the popped nodes of all of them in one
     launch, deduplicates, evaluates the survivors of all instances in ONE heuristic call and pushes -- the flattened batch of
-    astar.py:107-113 / :186, without leaving HBM.  One host round trip per step (the instance records)."""
+    astar.py:107-113 / :186, without leaving HBM.  One host round trip per step (the instance records).
+    Every instance keeps its own weight.  (The reference zips `self.weights` with the FILTERED instance list, astar.py:277: with unequal
+    weights an instance takes over a neighbour's weight as soon as an earlier instance has found its goal.  Equal weights -- every caller in
+    the reference -- are unaffected.)"""
 
     def __init__(self, states: List[State], env: Environment, heuristic_fn: Callable, weights: List[float],
                  max_nodes: Optional[int] = None):
