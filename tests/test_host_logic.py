@@ -272,3 +272,51 @@ def test_folded_network_equals_reference_module_fp32():
         ref = m(x)[:, 0]
     got = FoldedResnet(m, "fp32")(x)
     assert torch.allclose(ref, got, atol=2e-5, rtol=1e-5)
+
+
+def test_closed_four_phase_rule_equals_the_sequential_loop():
+    """The CLOSED kernels (closed_table.cu) settle a whole batch with four data-parallel phases -- probe (record the pre-batch value),
+    min (fold (g, id) of the candidates that beat it), resolve (winner / earlier-and-cheaper winner / left to the fix-up), fix-up
+    (running minimum among the few that came before their state's winner).  Pure-Python model of those phases against the
+    reference's child-order loop (parallel_weighted_astar.cpp:246-261; remove_in_closed, astar.py:78-90) on random batches with
+    many repeated states and depths."""
+    rng = np.random.RandomState(7)
+    table = {}                                            # state -> (g, id): what the slots hold
+    seq = {}                                              # the reference's dict: state -> best g
+    next_id = 0
+    for rnd in range(40):
+        m = int(rng.randint(1, 400))
+        states = rng.randint(0, 60, m)                    # few distinct states: many in-batch duplicates
+        g = rng.randint(1, 9, m)
+        ids = np.arange(next_id, next_id + m)
+        next_id += m
+        # reference: sequential in child order
+        keep_ref = np.zeros(m, bool)
+        for i in range(m):
+            if states[i] not in seq or seq[states[i]] > g[i]:
+                seq[states[i]] = g[i]; keep_ref[i] = True
+        # phase 1: probe -- every candidate records the slot's value BEFORE the batch
+        prev = [table.get(s) for s in states]
+        # phase 2: min -- candidates that beat the recorded value fold (g, id) into the slot
+        for i in range(m):
+            if prev[i] is None or g[i] < prev[i][0]:
+                cur = table.get(states[i])
+                if cur is None or (g[i], ids[i]) < cur:
+                    table[states[i]] = (g[i], ids[i])
+        # phase 3: resolve
+        keep = np.zeros(m, bool)
+        amb = []
+        for i in range(m):
+            if prev[i] is not None and g[i] >= prev[i][0]:
+                continue                                  # not cheaper than what CLOSED held: dropped
+            win = table[states[i]]
+            if win == (g[i], ids[i]):
+                keep[i] = True
+            elif win[1] > ids[i]:
+                amb.append(i)                             # came BEFORE the winner with a larger g
+        # phase 4: fix-up -- kept iff no earlier candidate of the same state on the list is at least as cheap
+        for i in amb:
+            if not any(states[j] == states[i] and ids[j] < ids[i] and g[j] <= g[i] for j in amb):
+                keep[i] = True
+        assert np.array_equal(keep, keep_ref), "round %d" % rnd
+        assert {s: v[0] for s, v in table.items()} == seq
