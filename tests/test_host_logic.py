@@ -320,3 +320,33 @@ def test_closed_four_phase_rule_equals_the_sequential_loop():
                 keep[i] = True
         assert np.array_equal(keep, keep_ref), "round %d" % rnd
         assert {s: v[0] for s, v in table.items()} == seq
+
+
+def test_ctypes_mirrors_match_the_header_layout(tmp_path):
+    """The Python mirrors of the ABI structs (deepcubea_b200/_lib.py) against include/dcb.h compiled with gcc: sizes and the offsets
+    of every field a binding touches."""
+    import ctypes
+    import subprocess
+    from deepcubea_b200 import _lib
+    fields = {"dcb_search_inst": ["open_size", "n_popped", "n_expand", "goal_id", "goal_key", "done", "n_goals", "next_slot", "iterations",
+                                  "nodes_generated", "nodes_expanded", "thr_key", "n_take", "resting", "overflow", "thr_lo"],
+              "dcb_step_plan": ["n_tiles", "n_parents", "n_kept", "closed_entries", "n_running", "error", "budget", "total_kept", "total_expanded"],
+              "dcb_search_ctx": ["env", "semantics", "slots_per_inst", "open_per_inst", "closed_capacity", "d_arena", "d_closed", "d_open_key",
+                                 "d_open_id", "d_open_key_lo", "d_inst", "d_plan", "d_weights", "d_kept_ids", "d_closed_scratch"]}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "dcb.h"', 'int main(void) {']
+    for st, fs in fields.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (st, st))
+        for f in fs:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (st, f, st, f))
+    lines += ["return 0; }"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).splitlines())
+    mirrors = {"dcb_search_inst": _lib.SearchInst, "dcb_step_plan": _lib.StepPlan, "dcb_search_ctx": _lib.SearchCtx}
+    for st, fs in fields.items():
+        assert int(got[st]) == ctypes.sizeof(mirrors[st]), st
+        for f in fs:
+            assert int(got["%s.%s" % (st, f)]) == getattr(mirrors[st], f).offset, "%s.%s" % (st, f)
+    assert ctypes.sizeof(_lib.SearchInst) == 128 and ctypes.sizeof(_lib.StepPlan) == 64
