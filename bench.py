@@ -177,6 +177,18 @@ def build_heuristic(wl, device, precision: str):
     return DeviceHeuristic(FoldedResnet(model, mode=precision).to(device), chunk=1 << 17), src
 
 
+def interval_union(spans):
+    """Total length covered by a list of (start, end) intervals (overlaps counted once)."""
+    total, cur_s, cur_e = 0.0, None, None
+    for a, b in sorted(spans):
+        if cur_e is None or a > cur_e:
+            total += (cur_e - cur_s) if cur_e is not None else 0.0
+            cur_s, cur_e = a, b
+        else:
+            cur_e = max(cur_e, b)
+    return total + ((cur_e - cur_s) if cur_e is not None else 0.0)
+
+
 # =====================================================================================================
 class Lane:
     """One search engine on its own CUDA stream.  A GPU runs `--lanes` of them side by side on independent problem instances:
@@ -364,14 +376,7 @@ def run_ours(args):
         # the wait too.  The tensor cores' busy time is the UNION of the launches' [start, end] intervals on the device clock.
         spans = sorted((ev0.elapsed_time(a), ev0.elapsed_time(b)) for l in lanes for a, b, _ in l.heur.gemm_events)
         gemm_ev = spans
-        cur_s, cur_e = None, None
-        for a, b in spans:
-            if cur_e is None or a > cur_e:
-                gemm_busy_ms += (cur_e - cur_s) if cur_e is not None else 0.0
-                cur_s, cur_e = a, b
-            else:
-                cur_e = max(cur_e, b)
-        gemm_busy_ms += (cur_e - cur_s) if cur_e is not None else 0.0
+        gemm_busy_ms = interval_union(spans)
         gemm_flops = heur.flops_per_row * float(kept)       # algorithmic: every surviving child passes through every layer once
         n_nn = sum(l.heur.gemm_launches for l in lanes) - gemm0
         launches += n_nn + max(1, n_nn // 10)              # + the one-hot kernel of each forward pass

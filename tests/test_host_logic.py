@@ -350,3 +350,23 @@ def test_ctypes_mirrors_match_the_header_layout(tmp_path):
         for f in fs:
             assert int(got["%s.%s" % (st, f)]) == getattr(mirrors[st], f).offset, "%s.%s" % (st, f)
     assert ctypes.sizeof(_lib.SearchInst) == 128 and ctypes.sizeof(_lib.StepPlan) == 64
+
+
+def test_bench_arms_share_one_state_list_and_interval_union():
+    """bench.py: both arms draw the SAME seeded start states (the reference arm may run on a GPU-less host: the checker's numpy port
+    of the reference generator gives the list the GPU-backed environment gives, tests/test_gpu_cli.py), scrambles of depth >= 20 only,
+    prefix-stable in the number asked for; and the union-of-intervals helper behind the GEMM busy time."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a, desc_a = bench.workload_states("cube3", 8)
+    b, desc_b = bench.workload_states("cube3", 24)
+    assert a.shape == (8, 54) and b.shape == (24, 54) and np.array_equal(a, b[:8])          # rank r of N takes b[r::N]: same list for every N
+    assert "seed %d" % bench.SEED in desc_a and "depth >= %d" % bench.MIN_SCRAMBLE in desc_a
+    env = O.OracleCube3()
+    np.random.seed(bench.SEED); random.seed(bench.SEED)
+    st, depths = env.generate_states(bench.POOL, (0, 26))
+    keep = np.nonzero(np.asarray(depths) >= bench.MIN_SCRAMBLE)[0]
+    assert np.array_equal(a, st[keep[:8]])
+    assert bench.interval_union([]) == 0.0
+    assert bench.interval_union([(0.0, 1.0), (2.0, 3.0)]) == 2.0
+    assert bench.interval_union([(0.0, 2.0), (1.0, 3.0), (2.5, 2.75), (5.0, 6.0)]) == 4.0
